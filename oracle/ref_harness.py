@@ -1,0 +1,115 @@
+"""TEST INFRASTRUCTURE — not product code.  Drives the *unmodified* reference (autonomousvision/gta,
+mounted read-only at /root/reference) to validate the oracle restatements and to generate the
+golden vectors under tests/golden/.  Only usable in the build container: /root/reference does not
+exist on the GPU box, so nothing under `-m gpu`, smoke() or bench.py imports this module.
+
+What it calls in the reference (no reference source is copied here):
+  * ImprovedSRTEncoder.pre_compute_reps   source/encoder.py:183-265   (self-attention reps)
+  * ImprovedSRTDecoder.pre_compute_reps   source/decoder.py:247-353   (cross-attention query reps)
+  * multihead_geometric_transform_attention  source/utils/gta.py:92-279
+  * AttnFn == softmax(q k^T * scale / tau) v   source/layers.py:202-211 (re-stated inline below
+    because the class is local to Attention.__init__)
+
+Import quirks handled: J_dense.pt is loaded from a CWD-relative path at import
+time, and source.encoder imports a symbol `ray2rotation` that does not exist at this commit.
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+import sys
+import types
+
+import torch
+
+REF_ROOT = os.environ.get("GTA_REF", "/root/reference")
+_mods = None
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF_ROOT, "source", "utils", "gta.py"))
+
+
+@contextlib.contextmanager
+def _cwd(path):
+    old = os.getcwd()
+    os.chdir(path)
+    try:
+        yield
+    finally:
+        os.chdir(old)
+
+
+def load():
+    """Import the reference modules once; returns a namespace with gta, wigner_d, encoder, decoder."""
+    global _mods
+    if _mods is not None:
+        return _mods
+    if not available():
+        raise RuntimeError("reference tree not found at %s" % REF_ROOT)
+    sys.dont_write_bytecode = True
+    with _cwd(REF_ROOT):
+        sys.path.insert(0, REF_ROOT)
+        try:
+            import source.utils.gta as rgta
+            if not hasattr(rgta, "ray2rotation"):
+                def _stub(*a, **k):
+                    raise NotImplementedError("ray2rotation is undefined in the reference")
+                rgta.ray2rotation = _stub
+            import source.utils.wigner_d as rwig
+            import source.encoder as renc
+            import source.decoder as rdec
+        finally:
+            sys.path.remove(REF_ROOT)
+    _mods = types.SimpleNamespace(gta=rgta, wigner_d=rwig, encoder=renc, decoder=rdec)
+    return _mods
+
+
+class _AttnFn:
+    """softmax(q k^T * scale / tau) v — what AttnFn.forward computes (source/layers.py:207-211)."""
+
+    def __init__(self, scale, tau=1.0):
+        self.scale, self.tau = scale, tau
+
+    def __call__(self, q, k, v):
+        sim = q @ k.transpose(-1, -2)
+        attn = torch.softmax(sim * self.scale / self.tau, dim=-1)
+        return attn @ v, attn
+
+
+def attn_args(cfg):
+    a = dict(f_dims=dict(cfg.f_dims), so2=cfg.so2, so3=cfg.so3, max_freq_h=cfg.max_freq_h,
+             max_freq_w=cfg.max_freq_w, shared_freqs=cfg.shared_freqs)
+    return a
+
+
+def ref_reps(cfg, extr_q, extr_k, coord_q, coord_k, cross: bool):
+    """Run the reference's own pre_compute_reps and return its `extras` dict."""
+    m = load()
+    extras = {}
+    B = extr_k.shape[0]
+    Nk, Nq = extr_k.shape[1], extr_q.shape[1]
+    extras["input_transforms"] = extr_k
+    extras["input_coord"] = coord_k.reshape(B, Nk, -1, 2)
+    enc = m.encoder.ImprovedSRTEncoder.__new__(m.encoder.ImprovedSRTEncoder)
+    m.encoder.ImprovedSRTEncoder.pre_compute_reps(enc, attn_args(cfg), extras)
+    if cross:
+        extras["target_transforms"] = extr_q
+        extras["target_coord"] = coord_q.reshape(B, Nq, -1, 2)
+        dec = m.decoder.ImprovedSRTDecoder.__new__(m.decoder.ImprovedSRTDecoder)
+        m.decoder.ImprovedSRTDecoder.pre_compute_reps(dec, attn_args(cfg), extras)
+    return extras
+
+
+def ref_gta_attention(cfg, inp, trans_coeff=0.01, tau=1.0, dtype=torch.float32):
+    """Reference forward on the given inputs (dict from gta_b200.synth.make_inputs)."""
+    m = load()
+    cross = inp["extr_q"] is not inp["extr_k"]
+    c = lambda t: t.to(dtype)
+    extras = ref_reps(cfg, c(inp["extr_q"]), c(inp["extr_k"]), c(inp["coord_q"]), c(inp["coord_k"]), cross)
+    fn = _AttnFn(cfg.head_dim ** -0.5, tau)
+    tc = torch.tensor([trans_coeff], dtype=dtype)
+    out, attn = m.gta.multihead_geometric_transform_attention(
+        c(inp["q"]), c(inp["k"]), c(inp["v"]), attn_fn=fn, f_dims=dict(cfg.f_dims), reps=extras,
+        trans_coeff=tc, v_transform=cfg.v_transform, euclid=False)
+    return out, extras
