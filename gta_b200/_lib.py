@@ -1,0 +1,75 @@
+"""ctypes binding of libgta_b200.so (C ABI declared in include/gta_b200.h).
+
+The library is built in-tree by `python -m gta_b200.build` (nvcc, sm_100a).  Loading fails loudly when the
+shared object is missing: there is no CPU / PyTorch fallback on the product path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgta_b200.so")
+
+GTA_DTYPE_BF16, GTA_DTYPE_F32 = 0, 1
+GTA_FLAG_P_IN_TMEM = 1
+GTA_FLAG_SKIP_STAGE = 2
+GTA_FLAG_STAGE_ONLY = 4
+
+
+class GtaReps(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("se3_q", "se3_k", "so3_q", "so3_k", "so2_q", "so2_k")]
+
+
+class GtaAttnParams(ctypes.Structure):
+    _fields_ = (
+        [("q", c_void_p), ("k", c_void_p), ("v", c_void_p)]
+        + [(n, c_int64) for n in ("q_stride_b", "q_stride_h", "q_stride_t", "k_stride_b", "k_stride_h",
+                                  "k_stride_t", "v_stride_b", "v_stride_h", "v_stride_t")]
+        + [("out", c_void_p), ("lse", c_void_p)]
+        + [(n, c_int) for n in ("B", "H", "Tq", "Tk", "D", "Nq", "Nk", "triv", "se3", "so3", "so2")]
+        + [("reps", GtaReps), ("trans_coeff", c_void_p), ("scale", c_float)]
+        + [(n, c_int) for n in ("in_dtype", "out_dtype", "v_transform")]
+        + [("workspace", c_void_p), ("workspace_bytes", c_size_t), ("flags", c_int)]
+    )
+
+
+# every symbol include/gta_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "gta_attn_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gta_attn_fwd": (c_int, [POINTER(GtaAttnParams), c_void_p]),
+    "gta_rotate_debug": (c_int, [POINTER(GtaAttnParams), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gta_build_reps": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_float, c_float, c_int, c_int] + [c_void_p] * 7),
+    "gta_so2_mats": (c_int, [c_void_p, c_int64, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),
+    "gta_wigner_d": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gta_umma_probe": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 3),
+    "gta_last_error": (c_char_p, []),
+    "gta_abi_version": (c_int, []),
+}
+
+_lib = None
+
+
+class GtaError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GtaError(
+                "gta_b200: %s is missing — build it with `python -m gta_b200.build` (needs nvcc). "
+                "There is no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(l, name)            # AttributeError if the .so does not export it
+            fn.restype, fn.argtypes = res, args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise GtaError("%s failed (rc=%d): %s" % (what or "gta_b200 call", rc, lib().gta_last_error().decode()))

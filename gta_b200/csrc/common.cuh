@@ -1,0 +1,35 @@
+// Shared host-side helpers of the C-ABI library (error reporting, launch checks) + internal launchers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/gta_b200.h"
+
+namespace gta {
+
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+int launch_build_reps(const float* extr_q, const float* extr_k, const float* coord_q, const float* coord_k, int B,
+                      int Nq, int Nk, int Tq, int Tk, int so2_nfreqs, float mfh, float mfw, int shared,
+                      int so3_maxdeg, float* se3_q, float* se3_k, float* so3_q, float* so3_k, float* so2_q,
+                      float* so2_k, cudaStream_t st);
+int launch_so2_mats(const float* coord, int64_t n, int nfreqs, float mfh, float mfw, int shared, float* mats,
+                    cudaStream_t st);
+int launch_wigner(const float* R, int64_t n, float* d1, float* d2, cudaStream_t st);
+
+int validate_attn_params(const GtaAttnParams* p);
+int launch_rotate_kv(const GtaAttnParams& p, cudaStream_t st);
+int launch_rotate_debug(const GtaAttnParams& p, float* qt, float* kt, float* vt, cudaStream_t st);
+int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st);
+int launch_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem, float* outS,
+                      float* outO, cudaStream_t st);
+
+// Scratch layout: [K' tiles | V' tiles], each tile image = D/32 column blocks x 128 rows x 64 B (bf16).
+inline int num_kv_tiles(int Tk) { return (Tk + 127) / 128; }
+inline size_t kv_tile_bytes(int D) { return static_cast<size_t>(128) * D * 2; }
+
+}  // namespace gta

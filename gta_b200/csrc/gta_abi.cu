@@ -1,0 +1,114 @@
+// extern "C" entry points of libgta_b200.so (declared in include/gta_b200.h).  Plain pointers and sizes only.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace gta {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return GTA_OK;
+}
+
+int validate_attn_params(const GtaAttnParams* p) {
+    if (!p) return set_error(GTA_ERR_INVALID, "null params");
+    if (!p->q || !p->k || !p->v || !p->out) return set_error(GTA_ERR_INVALID, "null q/k/v/out pointer");
+    if (p->B <= 0 || p->H <= 0 || p->Tq <= 0 || p->Tk <= 0) return set_error(GTA_ERR_INVALID, "empty B/H/Tq/Tk");
+    if (p->D != 32 && p->D != 64 && p->D != 96 && p->D != 128)
+        return set_error(GTA_ERR_UNSUPPORTED, "head dim %d not in {32,64,96,128}", p->D);
+    if (p->triv < 0 || p->se3 < 0 || p->so3 < 0 || p->so2 < 0 || p->triv + p->se3 + p->so3 + p->so2 != p->D)
+        return set_error(GTA_ERR_INVALID, "f_dims (%d,%d,%d,%d) must sum to head dim %d", p->triv, p->se3, p->so3,
+                         p->so2, p->D);
+    if ((p->triv | p->se3 | p->so3 | p->so2) & 7)
+        return set_error(GTA_ERR_UNSUPPORTED, "every f_dims block must be a multiple of 8 elements");
+    if (p->Nq <= 0 || p->Nk <= 0 || p->Tq % p->Nq || p->Tk % p->Nk)
+        return set_error(GTA_ERR_INVALID, "Tq/Tk must be divisible by the number of views");
+    if (p->se3 && (!p->reps.se3_q || !p->reps.se3_k)) return set_error(GTA_ERR_INVALID, "se3 block without se3 reps");
+    if (p->so3 && (!p->reps.so3_q || !p->reps.so3_k)) return set_error(GTA_ERR_INVALID, "so3 block without so3 reps");
+    if (p->so2 && (!p->reps.so2_q || !p->reps.so2_k)) return set_error(GTA_ERR_INVALID, "so2 block without so2 reps");
+    if ((p->in_dtype != GTA_DTYPE_BF16 && p->in_dtype != GTA_DTYPE_F32) ||
+        (p->out_dtype != GTA_DTYPE_BF16 && p->out_dtype != GTA_DTYPE_F32))
+        return set_error(GTA_ERR_UNSUPPORTED, "dtype must be bf16 or f32");
+    const int64_t align = p->in_dtype == GTA_DTYPE_BF16 ? 8 : 4;  // 16-byte vector loads
+    const int64_t strides[9] = {p->q_stride_b, p->q_stride_h, p->q_stride_t, p->k_stride_b, p->k_stride_h,
+                                p->k_stride_t, p->v_stride_b, p->v_stride_h, p->v_stride_t};
+    for (int i = 0; i < 9; ++i)
+        if (strides[i] % align) return set_error(GTA_ERR_UNSUPPORTED, "q/k/v strides must keep rows 16-byte aligned");
+    const uintptr_t ptrs[4] = {reinterpret_cast<uintptr_t>(p->q), reinterpret_cast<uintptr_t>(p->k),
+                               reinterpret_cast<uintptr_t>(p->v), reinterpret_cast<uintptr_t>(p->out)};
+    for (int i = 0; i < 4; ++i)
+        if (ptrs[i] & 15) return set_error(GTA_ERR_UNSUPPORTED, "q/k/v/out must be 16-byte aligned");
+    return GTA_OK;
+}
+
+}  // namespace gta
+
+using namespace gta;
+
+extern "C" {
+
+const char* gta_last_error(void) { return g_err; }
+int gta_abi_version(void) { return 1; }
+
+size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D) {
+    if (B <= 0 || H <= 0 || Tk <= 0 || D <= 0) return 0;
+    return 2 * static_cast<size_t>(B) * H * num_kv_tiles(Tk) * kv_tile_bytes(D);
+}
+
+int gta_attn_fwd(const GtaAttnParams* p, void* stream) {
+    int rc = validate_attn_params(p);
+    if (rc) return rc;
+    if (!p->workspace || p->workspace_bytes < gta_attn_fwd_workspace_bytes(p->B, p->H, p->Tk, p->D))
+        return set_error(GTA_ERR_INVALID, "workspace too small (need %zu bytes)",
+                         gta_attn_fwd_workspace_bytes(p->B, p->H, p->Tk, p->D));
+    if (reinterpret_cast<uintptr_t>(p->workspace) & 1023) return set_error(GTA_ERR_INVALID, "workspace must be 1024-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!(p->flags & GTA_FLAG_SKIP_STAGE)) {
+        rc = launch_rotate_kv(*p, st);
+        if (rc) return rc;
+    }
+    if (p->flags & GTA_FLAG_STAGE_ONLY) return GTA_OK;
+    return launch_attn_fwd(*p, st);
+}
+
+int gta_rotate_debug(const GtaAttnParams* p, float* qt, float* kt, float* vt, void* stream) {
+    int rc = validate_attn_params(p);
+    if (rc) return rc;
+    return launch_rotate_debug(*p, qt, kt, vt, static_cast<cudaStream_t>(stream));
+}
+
+int gta_build_reps(const float* extr_q, const float* extr_k, const float* coord_q, const float* coord_k, int B, int Nq,
+                   int Nk, int Tq, int Tk, int so2_nfreqs, float max_freq_h, float max_freq_w, int shared_freqs,
+                   int so3_maxdeg, float* se3_q, float* se3_k, float* so3_q, float* so3_k, float* so2_q, float* so2_k,
+                   void* stream) {
+    return launch_build_reps(extr_q, extr_k, coord_q, coord_k, B, Nq, Nk, Tq, Tk, so2_nfreqs, max_freq_h, max_freq_w,
+                             shared_freqs, so3_maxdeg, se3_q, se3_k, so3_q, so3_k, so2_q, so2_k,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int gta_so2_mats(const float* coord, int64_t n, int nfreqs, float max_freq_h, float max_freq_w, int shared_freqs,
+                 float* mats, void* stream) {
+    return launch_so2_mats(coord, n, nfreqs, max_freq_h, max_freq_w, shared_freqs, mats, static_cast<cudaStream_t>(stream));
+}
+
+int gta_wigner_d(const float* R, int64_t n, float* d1, float* d2, void* stream) {
+    return launch_wigner(R, n, d1, d2, static_cast<cudaStream_t>(stream));
+}
+
+int gta_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem, float* outS,
+                   float* outO, void* stream) {
+    return launch_umma_probe(A, Bm, P, V, D, p_in_tmem, outS, outO, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

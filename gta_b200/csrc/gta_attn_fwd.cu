@@ -1,0 +1,492 @@
+// Fused GTA attention forward for sm_100a.
+//
+//   O = rho_q^{-1} softmax((rho_q^{-T} Q)(K')^T * scale) V'      K' = rho_k K, V' = rho_k V (staged tiles)
+//
+// One CTA per (batch, head, 128-query tile); 6 warps:
+//   warps 0-3  softmax/correction/epilogue — thread i owns query row i == TMEM lane i.  Prologue: load the raw
+//              (strided) Q row, apply rho_q^{-T} in fp32 registers, write the bf16 UMMA operand tile.
+//              Epilogue: O/l, apply rho_q^{-1} in registers, store [B,Tq,H,D].
+//   warp 4     UMMA issuer (one lane): S = Q'K'^T (SS, M=128,N=128,K=16 x D/16) into a double-buffered TMEM
+//              accumulator, O += P V' (M=128,N=D,K=16 x 8) with P from shared memory (SS) or tensor memory (TS).
+//   warp 5     bulk-copy producer: one cp.async.bulk per K'/V' tile image into a 2-stage ring.
+// All producer/consumer hand-offs are mbarriers; tcgen05.commit signals MMA completion.
+//
+// Reference semantics: source/utils/gta.py:92-279 and source/layers.py:202-211.
+#include <cmath>
+
+#include "common.cuh"
+#include "reps.cuh"
+
+namespace gta {
+
+constexpr int kThreads = 192;
+constexpr int kStages = 2;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemS0 = 0, kTmemS1 = 128, kTmemO = 256;
+
+// K-step kk (16 elements of the head dim) of a K-major operand tile (Q' or K'), 64B swizzle:
+// 8-row groups are 512 B apart (SBO); inside a 64-byte row the step advances the start address by 32 B.
+__device__ __forceinline__ uint64_t desc_kmajor_sw64(uint32_t tile_addr, int kk) {
+    return make_smem_desc(tile_addr + (kk >> 1) * 8192u + (kk & 1) * 32u, 16u, 512u, kLayoutSW64);
+}
+// K-step kk (16 keys) of the MN-major V' tile: N (head dim) is contiguous in 32-element atoms 8192 B apart
+// (LBO); the 8-key groups along K are 512 B apart (SBO); 16 keys = 1024 B.
+__device__ __forceinline__ uint64_t desc_mnmajor_sw64(uint32_t tile_addr, int kk) {
+    return make_smem_desc(tile_addr + kk * 1024u, 8192u, 512u, kLayoutSW64);
+}
+// K-step kk (16 keys) of the K-major P tile (128B swizzle, 64-key column blocks 16 KB apart).
+__device__ __forceinline__ uint64_t desc_p_sw128(uint32_t p_addr, int kk) {
+    return make_smem_desc(p_addr + (kk >> 2) * 16384u + (kk & 3) * 32u, 16u, 1024u, kLayoutSW128);
+}
+
+struct AttnArgs {
+    const void* q;
+    int64_t q_sb, q_sh, q_st;
+    void* out;
+    float* lse;
+    const uint8_t* ws_k;
+    const uint8_t* ws_v;
+    int B, H, Tq, Tk, Nq, tpvq, ntiles_k, C;
+    HeadDims hd;
+    const float* se3_q;
+    const float* so3_q;
+    const float* so2_q;
+    const float* tc_ptr;
+    float scale, scale_log2;
+    int v_transform;
+};
+
+enum BarIdx {
+    kBarQFull = 0,
+    kBarKFull = 1,                       // [kStages]
+    kBarVFull = kBarKFull + kStages,     // [kStages]
+    kBarKEmpty = kBarVFull + kStages,    // [kStages]
+    kBarVEmpty = kBarKEmpty + kStages,   // [kStages]
+    kBarSFull = kBarVEmpty + kStages,    // [2]
+    kBarPFull = kBarSFull + 2,           // [2]
+    kBarPVDone = kBarPFull + 2,
+    kNumBars
+};
+
+template <int D, bool P_TMEM>
+struct AttnSmem {
+    static constexpr uint32_t kTile = 128u * D * 2u;
+    static constexpr uint32_t kQ = 0;
+    static constexpr uint32_t kK = kTile;
+    static constexpr uint32_t kV = kTile * (1 + kStages);
+    static constexpr uint32_t kP = kTile * (1 + 2 * kStages);
+    static constexpr uint32_t kBars = kP + (P_TMEM ? 0u : 32768u);
+    static constexpr uint32_t kTmemSlot = kBars + kNumBars * 8;
+    static constexpr uint32_t kUsed = kTmemSlot + 16;
+    // >= 120 KB so that only one CTA (one 512-column TMEM allocation) is resident per SM
+    static constexpr uint32_t kBytes = (kUsed + 1024 > 120u * 1024u) ? kUsed + 1024 : 120u * 1024u;
+};
+
+template <typename TIn, typename TOut, int D, bool P_TMEM>
+__global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const AttnArgs a) {
+    using L = AttnSmem<D, P_TMEM>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
+
+    const int qtile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = a.ntiles_k;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[kBarQFull], 128);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bars[kBarKFull + s], 1);
+            mbar_init(&bars[kBarVFull + s], 1);
+            mbar_init(&bars[kBarKEmpty + s], 1);
+            mbar_init(&bars[kBarVEmpty + s], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[kBarSFull + i], 1);
+            mbar_init(&bars[kBarPFull + i], 128);
+        }
+        mbar_init(&bars[kBarPVDone], 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp < 4) {
+        // =========================================================== softmax / correction / epilogue
+        const int r = threadIdx.x;
+        const int t = qtile * 128 + r;
+        const bool valid = t < a.Tq;
+        const int tt = valid ? t : a.Tq - 1;
+        const float tc = a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f;
+        const size_t view = static_cast<size_t>(b) * a.Nq + tt / a.tpvq;
+        const float* se3 = a.se3_q + view * 16;
+        const float* so3 = a.so3_q + view * 34;
+        const float* so2 = a.so2_q + (static_cast<size_t>(b) * a.Tq + tt) * a.C * 2;
+
+        {   // ---- Q prologue: raw row -> rho_q^{-T} -> bf16 operand tile
+            const TIn* qrow = reinterpret_cast<const TIn*>(a.q) + static_cast<int64_t>(b) * a.q_sb +
+                              static_cast<int64_t>(h) * a.q_sh + static_cast<int64_t>(tt) * a.q_st;
+#pragma unroll 1
+            for (int c = 0; c < D / 8; ++c) {
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = 0.f;
+                if (valid) {
+                    load_chunk<TIn>(qrow + c * 8, x);
+                    apply_rep_chunk<kModeQ>(x, c, a.hd, se3, so3, so2, tc);
+                }
+                *reinterpret_cast<uint4*>(smem + L::kQ + tile_sw64_offset(r, c)) = pack_chunk_bf16(x);
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&bars[kBarQFull]);
+        }
+
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const float cs = a.scale_log2;
+        float m_run = -INFINITY, l_run = 0.f;
+
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            const int buf = j & 1;
+            mbar_wait(&bars[kBarSFull + buf], (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t sreg[128];
+            const uint32_t s_addr = lane_base + (buf ? kTmemS1 : kTmemS0);
+            tmem_ld32(s_addr, sreg);
+            tmem_ld32(s_addr + 32, sreg + 32);
+            tmem_ld32(s_addr + 64, sreg + 64);
+            tmem_ld32(s_addr + 96, sreg + 96);
+            tmem_ld_wait();
+            float* s = reinterpret_cast<float*>(sreg);
+            if (j == n - 1) {
+                const int nvalid = a.Tk - j * 128;
+                if (nvalid < 128) {
+#pragma unroll
+                    for (int i = 0; i < 128; ++i) if (i >= nvalid) s[i] = -INFINITY;
+                }
+            }
+            float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+            for (int i = 4; i < 128; i += 4) {
+                mx0 = fmaxf(mx0, s[i]); mx1 = fmaxf(mx1, s[i + 1]);
+                mx2 = fmaxf(mx2, s[i + 2]); mx3 = fmaxf(mx3, s[i + 3]);
+            }
+            const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+            const float alpha = fast_exp2((m_run - m_new) * cs);
+
+            if (j > 0) {
+                // O of tiles < j must be complete before it is rescaled / before P is overwritten.
+                mbar_wait(&bars[kBarPVDone], (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+                    for (int cb = 0; cb < D / 32; ++cb) {
+                        uint32_t o[32];
+                        tmem_ld32(lane_base + kTmemO + cb * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(lane_base + kTmemO + cb * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+            }
+
+            const float neg = -m_new * cs;
+            float ls0 = 0.f, ls1 = 0.f;
+            if (P_TMEM) {
+                // P (bf16, two keys per 32-bit column) overwrites the first 64 columns of this S buffer.
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t pr[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        float p0 = fast_exp2(fmaf(s[half * 64 + 2 * i], cs, neg));
+                        float p1 = fast_exp2(fmaf(s[half * 64 + 2 * i + 1], cs, neg));
+                        ls0 += p0; ls1 += p1;
+                        pr[i] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st32(s_addr + half * 32, pr);
+                }
+                tmem_st_wait();
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    float p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) p[i] = fast_exp2(fmaf(s[c * 8 + i], cs, neg));
+                    ls0 += (p[0] + p[2]) + (p[4] + p[6]);
+                    ls1 += (p[1] + p[3]) + (p[5] + p[7]);
+                    *reinterpret_cast<uint4*>(smem + L::kP + tile_sw128_offset(r, c)) = pack_chunk_bf16(p);
+                }
+                fence_proxy_async_smem();
+            }
+            l_run = fmaf(l_run, alpha, ls0 + ls1);
+            m_run = m_new;
+            tc_fence_before();
+            mbar_arrive(&bars[kBarPFull + buf]);
+        }
+
+        // ---- epilogue: O / l, rho_q^{-1}, store [B,Tq,H,D]
+        mbar_wait(&bars[kBarPVDone], (n - 1) & 1);
+        tc_fence_after();
+        const float inv_l = 1.0f / l_run;
+        TOut* orow = reinterpret_cast<TOut*>(a.out) + ((static_cast<int64_t>(b) * a.Tq + tt) * a.H + h) * D;
+#pragma unroll 1
+        for (int cb = 0; cb < D / 32; ++cb) {
+            uint32_t o[32];
+            tmem_ld32(lane_base + kTmemO + cb * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                float x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(o[cc * 8 + i]) * inv_l;
+                const int c = cb * 4 + cc;
+                if (a.v_transform) apply_rep_chunk<kModeOut>(x, c, a.hd, se3, so3, so2, tc);
+                if (valid) store_chunk<TOut>(orow + c * 8, x);
+            }
+        }
+        if (a.lse && valid)
+            a.lse[(static_cast<int64_t>(b) * a.H + h) * a.Tq + t] = m_run * a.scale + logf(l_run);
+        tc_fence_before();
+    } else if (warp == 4) {
+        // =========================================================== UMMA issuer
+        constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
+        const uint32_t q_addr = smem_u32(smem + L::kQ);
+        const uint32_t p_addr = smem_u32(smem + L::kP);
+        mbar_wait(&bars[kBarQFull], 0);
+        tc_fence_after();
+
+        auto issue_qk = [&](int j) {
+            const int s = j % kStages;
+            mbar_wait(&bars[kBarKFull + s], (j / kStages) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t k_addr = smem_u32(smem + L::kK + s * L::kTile);
+                const uint32_t d_addr = tmem_base + ((j & 1) ? kTmemS1 : kTmemS0);
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ss(d_addr, desc_kmajor_sw64(q_addr, kk), desc_kmajor_sw64(k_addr, kk), idesc_qk, kk > 0);
+                umma_commit(&bars[kBarKEmpty + s]);
+                umma_commit(&bars[kBarSFull + (j & 1)]);
+            }
+            __syncwarp();
+        };
+        auto issue_pv = [&](int j) {
+            const int s = j % kStages;
+            mbar_wait(&bars[kBarVFull + s], (j / kStages) & 1);
+            mbar_wait(&bars[kBarPFull + (j & 1)], (j >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t v_addr = smem_u32(smem + L::kV + s * L::kTile);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
+                    if (P_TMEM)
+                        umma_ts(tmem_base + kTmemO, tmem_base + ((j & 1) ? kTmemS1 : kTmemS0) + kk * 8,
+                                desc_mnmajor_sw64(v_addr, kk), idesc_pv, acc);
+                    else
+                        umma_ss(tmem_base + kTmemO, desc_p_sw128(p_addr, kk), desc_mnmajor_sw64(v_addr, kk),
+                                idesc_pv, acc);
+                }
+                umma_commit(&bars[kBarVEmpty + s]);
+                umma_commit(&bars[kBarPVDone]);
+            }
+            __syncwarp();
+        };
+        issue_qk(0);
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            if (j + 1 < n) issue_qk(j + 1);
+            issue_pv(j);
+        }
+    } else {
+        // =========================================================== bulk-copy producer
+        const size_t blob0 = (static_cast<size_t>(b) * a.H + h) * n;
+#pragma unroll 1
+        for (int j = 0; j < n; ++j) {
+            const int s = j % kStages;
+            if (j >= kStages) mbar_wait(&bars[kBarKEmpty + s], ((j / kStages) - 1) & 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars[kBarKFull + s], L::kTile);
+                bulk_g2s(smem + L::kK + s * L::kTile, a.ws_k + (blob0 + j) * L::kTile, L::kTile, &bars[kBarKFull + s]);
+            }
+            if (j >= kStages) mbar_wait(&bars[kBarVEmpty + s], ((j / kStages) - 1) & 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars[kBarVFull + s], L::kTile);
+                bulk_g2s(smem + L::kV + s * L::kTile, a.ws_v + (blob0 + j) * L::kTile, L::kTile, &bars[kBarVFull + s]);
+            }
+            __syncwarp();
+        }
+    }
+
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+template <typename TIn, typename TOut, int D, bool P_TMEM>
+static int launch_one(const AttnArgs& a, dim3 grid, cudaStream_t st) {
+    using L = AttnSmem<D, P_TMEM>;
+    auto kern = attn_fwd_kernel<TIn, TOut, D, P_TMEM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::kBytes));
+    if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    kern<<<grid, kThreads, L::kBytes, st>>>(a);
+    return check_launch("gta_attn_fwd");
+}
+
+template <typename TIn, typename TOut, bool P_TMEM>
+static int launch_d(const AttnArgs& a, int D, dim3 grid, cudaStream_t st) {
+    switch (D) {
+        case 32: return launch_one<TIn, TOut, 32, P_TMEM>(a, grid, st);
+        case 64: return launch_one<TIn, TOut, 64, P_TMEM>(a, grid, st);
+        case 96: return launch_one<TIn, TOut, 96, P_TMEM>(a, grid, st);
+        case 128: return launch_one<TIn, TOut, 128, P_TMEM>(a, grid, st);
+    }
+    return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_fwd: head dim %d not in {32,64,96,128}", D);
+}
+
+template <bool P_TMEM>
+static int launch_t(const GtaAttnParams& p, const AttnArgs& a, dim3 grid, cudaStream_t st) {
+    const bool ib = p.in_dtype == GTA_DTYPE_BF16, ob = p.out_dtype == GTA_DTYPE_BF16;
+    if (ib && ob) return launch_d<__nv_bfloat16, __nv_bfloat16, P_TMEM>(a, p.D, grid, st);
+    if (ib && !ob) return launch_d<__nv_bfloat16, float, P_TMEM>(a, p.D, grid, st);
+    if (!ib && ob) return launch_d<float, __nv_bfloat16, P_TMEM>(a, p.D, grid, st);
+    return launch_d<float, float, P_TMEM>(a, p.D, grid, st);
+}
+
+int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st) {
+    AttnArgs a;
+    a.q = p.q; a.q_sb = p.q_stride_b; a.q_sh = p.q_stride_h; a.q_st = p.q_stride_t;
+    a.out = p.out; a.lse = p.lse;
+    a.ntiles_k = num_kv_tiles(p.Tk);
+    const size_t half = static_cast<size_t>(p.B) * p.H * a.ntiles_k * kv_tile_bytes(p.D);
+    a.ws_k = static_cast<const uint8_t*>(p.workspace);
+    a.ws_v = a.ws_k + half;
+    a.B = p.B; a.H = p.H; a.Tq = p.Tq; a.Tk = p.Tk; a.Nq = p.Nq; a.tpvq = p.Tq / p.Nq;
+    a.C = p.so2 >> 1;
+    a.hd = HeadDims{p.triv, p.se3, p.so3, p.so2};
+    a.se3_q = p.reps.se3_q; a.so3_q = p.reps.so3_q; a.so2_q = p.reps.so2_q; a.tc_ptr = p.trans_coeff;
+    a.scale = p.scale;
+    a.scale_log2 = p.scale * 1.4426950408889634f;
+    a.v_transform = p.v_transform;
+    dim3 grid((p.Tq + 127) / 128, p.H, p.B);
+    if (p.flags & GTA_FLAG_P_IN_TMEM) return launch_t<true>(p, a, grid, st);
+    return launch_t<false>(p, a, grid, st);
+}
+
+// ===================================================================================================
+// tcgen05 self-test: one CTA, S = A B^T and O = P V through the same tile images + descriptors.
+template <int D, bool P_TMEM>
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __nv_bfloat16* __restrict__ A,
+                                                           const __nv_bfloat16* __restrict__ Bm,
+                                                           const __nv_bfloat16* __restrict__ P,
+                                                           const __nv_bfloat16* __restrict__ V, float* __restrict__ outS,
+                                                           float* __restrict__ outO) {
+    constexpr uint32_t kTile = 128u * D * 2u;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem; uint8_t* sB = smem + kTile; uint8_t* sV = smem + 2 * kTile; uint8_t* sP = smem + 3 * kTile;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 3 * kTile + 32768);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+    const int r = threadIdx.x, warp = r >> 5;
+    if (r == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); fence_mbar_init(); }
+    if (warp == 0) { tmem_alloc(slot, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *reinterpret_cast<volatile uint32_t*>(slot);
+    const uint32_t lane_base = tb + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int c = 0; c < D / 8; ++c) {
+        *reinterpret_cast<uint4*>(sA + tile_sw64_offset(r, c)) = *reinterpret_cast<const uint4*>(A + r * D + c * 8);
+        *reinterpret_cast<uint4*>(sB + tile_sw64_offset(r, c)) = *reinterpret_cast<const uint4*>(Bm + r * D + c * 8);
+        *reinterpret_cast<uint4*>(sV + tile_sw64_offset(r, c)) = *reinterpret_cast<const uint4*>(V + r * D + c * 8);
+    }
+    if (P_TMEM) {
+        uint32_t pr[32];
+        for (int half = 0; half < 2; ++half) {
+            for (int i = 0; i < 32; ++i) pr[i] = *reinterpret_cast<const uint32_t*>(P + r * 128 + half * 64 + 2 * i);
+            tmem_st32(lane_base + 128 + half * 32, pr);
+        }
+        tmem_st_wait();
+    } else {
+        for (int c = 0; c < 16; ++c)
+            *reinterpret_cast<uint4*>(sP + tile_sw128_offset(r, c)) = *reinterpret_cast<const uint4*>(P + r * 128 + c * 8);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (r == 0) {
+        constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
+        for (int kk = 0; kk < D / 16; ++kk)
+            umma_ss(tb + 0, desc_kmajor_sw64(smem_u32(sA), kk), desc_kmajor_sw64(smem_u32(sB), kk), idesc_qk, kk > 0);
+        umma_commit(&bar[0]);
+        for (int kk = 0; kk < 8; ++kk) {
+            if (P_TMEM) umma_ts(tb + 256, tb + 128 + kk * 8, desc_mnmajor_sw64(smem_u32(sV), kk), idesc_pv, kk > 0);
+            else umma_ss(tb + 256, desc_p_sw128(smem_u32(sP), kk), desc_mnmajor_sw64(smem_u32(sV), kk), idesc_pv, kk > 0);
+        }
+        umma_commit(&bar[1]);
+    }
+    __syncwarp();
+    mbar_wait(&bar[0], 0);
+    mbar_wait(&bar[1], 0);
+    tc_fence_after();
+    for (int cb = 0; cb < 4; ++cb) {
+        uint32_t o[32];
+        tmem_ld32(lane_base + cb * 32, o);
+        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) outS[r * 128 + cb * 32 + i] = __uint_as_float(o[i]);
+    }
+    for (int cb = 0; cb < D / 32; ++cb) {
+        uint32_t o[32];
+        tmem_ld32(lane_base + 256 + cb * 32, o);
+        tmem_ld_wait();
+        for (int i = 0; i < 32; ++i) outO[r * D + cb * 32 + i] = __uint_as_float(o[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
+template <int D, bool P_TMEM>
+static int probe_one(const void* A, const void* Bm, const void* P, const void* V, float* outS, float* outO,
+                     cudaStream_t st) {
+    auto kern = umma_probe_kernel<D, P_TMEM>;
+    const int bytes = 3 * 128 * D * 2 + 32768 + 64 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    kern<<<1, 128, bytes, st>>>(static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(Bm),
+                                static_cast<const __nv_bfloat16*>(P), static_cast<const __nv_bfloat16*>(V), outS, outO);
+    return check_launch("gta_umma_probe");
+}
+
+int launch_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem, float* outS,
+                      float* outO, cudaStream_t st) {
+#define GTA_PROBE_CASE(DD)                                                              \
+    case DD:                                                                            \
+        return p_in_tmem ? probe_one<DD, true>(A, Bm, P, V, outS, outO, st)             \
+                         : probe_one<DD, false>(A, Bm, P, V, outS, outO, st);
+    switch (D) {
+        GTA_PROBE_CASE(32)
+        GTA_PROBE_CASE(64)
+        GTA_PROBE_CASE(96)
+        GTA_PROBE_CASE(128)
+    }
+#undef GTA_PROBE_CASE
+    return set_error(GTA_ERR_UNSUPPORTED, "gta_umma_probe: head dim %d not in {32,64,96,128}", D);
+}
+
+}  // namespace gta

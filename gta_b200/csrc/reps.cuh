@@ -1,0 +1,155 @@
+// Block-diagonal representation application on 8-element chunks, in fp32 registers.
+//
+// A head row of D elements is [triv | se3 | so3 | so2] (reference: source/utils/gta.py:112-122); all
+// block boundaries are multiples of 8 elements for every shipped config (se3 % 4, so3 % 8, so2 = 4*nfreq),
+// and the host validates it, so one 16-byte bf16 chunk never straddles two block types:
+//   se3 chunk = two 4-vectors, each multiplied by the view's 4x4 (gta.py:160-167, :255-257)
+//   so3 chunk = [3 | 5] multiplied by Wigner D_1, D_2 of the view (gta.py:182-201, :259-268)
+//   so2 chunk = four (x,y) pairs, each rotated by the token's angle (gta.py:203-219, :269-271)
+#pragma once
+#include "ptx.cuh"
+
+namespace gta {
+
+enum RepMode : int {
+    kModeQ = 0,    // rho_q^{-T}: (E_q*msk)^T, D_q, R(th_q)
+    kModeKV = 1,   // rho_k:      inv(E_k)*msk, D_k, R(th_k)
+    kModeOut = 2,  // rho_q^{-1}: E_q*msk, D_q^T, R(th_q)^T
+};
+
+struct HeadDims {
+    int triv, se3, so3, so2;  // element counts; sum = D
+};
+
+// y = (M * scale_mask(tc)) x for two 4-vectors; M row-major 4x4 (unscaled), scale_mask multiplies the
+// translation column (rows 0..2 of column 3) by tc and zeroes row 3 except M33 (gta.py:40-44).
+__device__ __forceinline__ void se3_apply(float* x, const float* __restrict__ M, float tc) {
+    const float m03 = M[3] * tc, m13 = M[7] * tc, m23 = M[11] * tc, m33 = M[15];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        float a = x[4 * v], b = x[4 * v + 1], c = x[4 * v + 2], d = x[4 * v + 3];
+        x[4 * v + 0] = fmaf(M[0], a, fmaf(M[1], b, fmaf(M[2], c, m03 * d)));
+        x[4 * v + 1] = fmaf(M[4], a, fmaf(M[5], b, fmaf(M[6], c, m13 * d)));
+        x[4 * v + 2] = fmaf(M[8], a, fmaf(M[9], b, fmaf(M[10], c, m23 * d)));
+        x[4 * v + 3] = m33 * d;
+    }
+}
+// y = (M * scale_mask(tc))^T x
+__device__ __forceinline__ void se3_apply_T(float* x, const float* __restrict__ M, float tc) {
+    const float m33 = M[15];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        float a = x[4 * v], b = x[4 * v + 1], c = x[4 * v + 2], d = x[4 * v + 3];
+        x[4 * v + 0] = fmaf(M[0], a, fmaf(M[4], b, M[8] * c));
+        x[4 * v + 1] = fmaf(M[1], a, fmaf(M[5], b, M[9] * c));
+        x[4 * v + 2] = fmaf(M[2], a, fmaf(M[6], b, M[10] * c));
+        x[4 * v + 3] = fmaf(tc, fmaf(M[3], a, fmaf(M[7], b, M[11] * c)), m33 * d);
+    }
+}
+// W = D1 (9, row-major) | D2 (25, row-major); x = [3 | 5].
+template <bool kTranspose>
+__device__ __forceinline__ void so3_apply(float* x, const float* __restrict__ W) {
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) s = fmaf(kTranspose ? W[j * 3 + i] : W[i * 3 + j], x[j], s);
+        y[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) s = fmaf(kTranspose ? W[9 + j * 5 + i] : W[9 + i * 5 + j], x[3 + j], s);
+        y[3 + i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = y[i];
+}
+// cs = (cos, sin) x 4 pairs; R = [[c,-s],[s,c]]; inverse uses R^T.
+template <bool kInverse>
+__device__ __forceinline__ void so2_apply(float* x, const float* __restrict__ cs) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        float c = cs[2 * p], s = kInverse ? -cs[2 * p + 1] : cs[2 * p + 1];
+        float a = x[2 * p], b = x[2 * p + 1];
+        x[2 * p] = fmaf(c, a, -s * b);
+        x[2 * p + 1] = fmaf(s, a, c * b);
+    }
+}
+
+// Applies the rep of `mode` to chunk c (8 elements) of a head row.
+//   se3m: 16 floats of the token's view (E_q for kModeQ/kModeOut, inv(E_k) for kModeKV), unscaled
+//   so3m: 34 floats of the token's view;  so2cs: the token's [C][2] (cos,sin) table
+template <int kMode>
+__device__ __forceinline__ void apply_rep_chunk(float* x, int c, const HeadDims& hd, const float* __restrict__ se3m,
+                                                const float* __restrict__ so3m, const float* __restrict__ so2cs,
+                                                float tc) {
+    const int e = c * 8;
+    if (e < hd.triv) return;
+    if (e < hd.triv + hd.se3) {
+        float M[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 r = __ldg(reinterpret_cast<const float4*>(se3m) + i);
+            M[4 * i] = r.x; M[4 * i + 1] = r.y; M[4 * i + 2] = r.z; M[4 * i + 3] = r.w;
+        }
+        if (kMode == kModeQ) se3_apply_T(x, M, tc); else se3_apply(x, M, tc);
+        return;
+    }
+    if (e < hd.triv + hd.se3 + hd.so3) {
+        float W[34];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            float2 r = __ldg(reinterpret_cast<const float2*>(so3m) + i);
+            W[2 * i] = r.x; W[2 * i + 1] = r.y;
+        }
+        if (kMode == kModeOut) so3_apply<true>(x, W); else so3_apply<false>(x, W);
+        return;
+    }
+    {
+        const int pc = (e - hd.triv - hd.se3 - hd.so3) >> 1;  // first pair index of this chunk
+        float cs[8];
+        float4 r0 = __ldg(reinterpret_cast<const float4*>(so2cs + 2 * pc));
+        float4 r1 = __ldg(reinterpret_cast<const float4*>(so2cs + 2 * pc) + 1);
+        cs[0] = r0.x; cs[1] = r0.y; cs[2] = r0.z; cs[3] = r0.w;
+        cs[4] = r1.x; cs[5] = r1.y; cs[6] = r1.z; cs[7] = r1.w;
+        if (kMode == kModeOut) so2_apply<true>(x, cs); else so2_apply<false>(x, cs);
+    }
+}
+
+// 8 consecutive elements of a row -> fp32 registers (bf16 or fp32 source; 16-byte / 32-byte aligned).
+template <typename T>
+__device__ __forceinline__ void load_chunk(const T* __restrict__ p, float* x);
+template <>
+__device__ __forceinline__ void load_chunk<__nv_bfloat16>(const __nv_bfloat16* __restrict__ p, float* x) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    x[0] = bf16_lo(v.x); x[1] = bf16_hi(v.x); x[2] = bf16_lo(v.y); x[3] = bf16_hi(v.y);
+    x[4] = bf16_lo(v.z); x[5] = bf16_hi(v.z); x[6] = bf16_lo(v.w); x[7] = bf16_hi(v.w);
+}
+template <>
+__device__ __forceinline__ void load_chunk<float>(const float* __restrict__ p, float* x) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ uint4 pack_chunk_bf16(const float* x) {
+    uint4 v;
+    v.x = pack_bf16x2(x[0], x[1]); v.y = pack_bf16x2(x[2], x[3]);
+    v.z = pack_bf16x2(x[4], x[5]); v.w = pack_bf16x2(x[6], x[7]);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ void store_chunk(T* p, const float* x);
+template <>
+__device__ __forceinline__ void store_chunk<__nv_bfloat16>(__nv_bfloat16* p, const float* x) {
+    *reinterpret_cast<uint4*>(p) = pack_chunk_bf16(x);
+}
+template <>
+__device__ __forceinline__ void store_chunk<float>(float* p, const float* x) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(x[0], x[1], x[2], x[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(x[4], x[5], x[6], x[7]);
+}
+
+}  // namespace gta

@@ -1,0 +1,141 @@
+"""Host-side mirror of the reference's GTA operator interface (source/utils/gta.py), backed by the CUDA library.
+
+Same names, argument meaning and return convention as the reference so that it drops in behind
+`source.layers.Attention.forward` (source/layers.py:419-428) without touching encoder/decoder code:
+
+    import gta_b200.gta as fast
+    fast.install()        # rebinds source.layers.multihead_geometric_transform_attention (+ source.utils.gta)
+
+Forward only (inference / no_grad).  Calls that need autograd, the attention map, the `t2` block or the
+euclid similarity are delegated to the original reference function when it was captured by install(), and raise
+NotImplementedError otherwise — there is no silent CPU or PyTorch fallback inside this package.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import PackedReps
+from .synth import make_2dcoord  # noqa: F401  (same values as source/utils/gta.py:9-16)
+
+_original = None          # the reference implementation captured by install()
+_PACK_KEY = "_gta_b200_packed"
+
+
+def scale_mask(trans_coeff, device):
+    """[[1,1,1,tc]x3,[0,0,0,1]] (source/utils/gta.py:40-44); the kernels apply it on load."""
+    msk = torch.ones(4, 4, device=device)
+    msk[:3, 3] = msk[:3, 3] * torch.as_tensor(trans_coeff, device=device, dtype=torch.float32).reshape(())
+    msk[3, :3] = 0
+    return msk
+
+
+def make_SO2mats(coord, nfreqs, max_freqs=(1, 1), shared_freqs=False):
+    """coord [..., 2] -> [..., nfreqs, 2, 2, 2] exactly as source/utils/gta.py:47-69 returns it
+    (callers flatten dims -4,-3 into the pair index freq*2+axis, encoder.py:195)."""
+    if coord.shape[-1] != 2:
+        raise NotImplementedError("gta_b200.make_SO2mats: only 2-d coordinates are implemented")
+    m = ops.so2_mats(coord, nfreqs, max_freqs, shared_freqs)          # [..., 2*nfreqs, 2, 2]
+    return m.reshape(*coord.shape[:-1], nfreqs, 2, 2, 2)
+
+
+def _pack_reps(reps: dict, f_dims: dict, B: int) -> PackedReps:
+    """Reference-format rep tensors (the `extras` dict) -> packed fp32 tables.  Cached in the dict, keyed on the
+    identity of the source tensors (the decoder overwrites the *_q entries, decoder.py:259-346)."""
+    g = lambda n: int(f_dims.get(n, 0) or 0)
+    src = tuple(id(reps.get(n)) for n in ("inv_se3rep_q", "se3rep_k", "so3rep_q", "so3rep_k", "so2rep_q", "so2rep_k"))
+    hit = reps.get(_PACK_KEY)
+    if hit is not None and hit[0] == src:
+        return hit[1]
+    f = lambda t: t.detach().to(torch.float32)
+    p = PackedReps()
+    if g("se3"):
+        p.se3_q = f(reps["inv_se3rep_q"]).reshape(B, -1, 16).contiguous()
+        p.se3_k = f(reps["se3rep_k"]).reshape(B, -1, 16).contiguous()
+        p.n_q_views, p.n_k_views = p.se3_q.shape[1], p.se3_k.shape[1]
+    if g("so3"):
+        dq, dk = reps["so3rep_q"], reps["so3rep_k"]
+        if len(dq) != 2 or dq[0].shape[-1] != 3 or dq[1].shape[-1] != 5:
+            raise NotImplementedError("gta_b200: so3 reps must be [D_1, D_2]")
+        p.so3_q = torch.cat([f(dq[0]).reshape(B, -1, 9), f(dq[1]).reshape(B, -1, 25)], -1).contiguous()
+        p.so3_k = torch.cat([f(dk[0]).reshape(B, -1, 9), f(dk[1]).reshape(B, -1, 25)], -1).contiguous()
+        p.n_q_views, p.n_k_views = p.so3_q.shape[1], p.so3_k.shape[1]
+    if g("so2"):
+        def cs(m):  # [B,T,C,2,2] = [[c,-s],[s,c]] -> [B,T,C,2]
+            m = f(m)
+            return torch.stack([m[..., 0, 0], m[..., 1, 0]], -1).contiguous()
+        p.so2_q = cs(reps["so2rep_q"])
+        p.so2_k = p.so2_q if reps["so2rep_k"] is reps["so2rep_q"] else cs(reps["so2rep_k"])
+    reps[_PACK_KEY] = (src, p)
+    return p
+
+
+def _delegate(reason, *args, **kwargs):
+    if _original is None:
+        raise NotImplementedError("gta_b200: %s is not implemented by the fused path" % reason)
+    warnings.warn("gta_b200: %s -> delegating to the reference implementation" % reason, stacklevel=3)
+    return _original(*args, **kwargs)
+
+
+def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, trans_coeff=1.0, v_transform=True,
+                                            euclid=False, **kwargs):
+    """Drop-in for source/utils/gta.py:92-279.  q [B,H,Tq,C], k,v [B,H,Tk,C] (strided views are consumed
+    as they are); returns (out [B,H,Tq,C], None) — the attention map is never materialised."""
+    args = (q, k, v, attn_fn, f_dims, reps)
+    kw = dict(trans_coeff=trans_coeff, v_transform=v_transform, euclid=euclid, **kwargs)
+    g = lambda n: int(f_dims.get(n, 0) or 0)
+    if euclid:
+        return _delegate("euclid similarity", *args, **kw)
+    if g("t2"):
+        return _delegate("the t2 block", *args, **kw)
+    if not q.is_cuda:
+        return _delegate("a non-CUDA tensor", *args, **kw)
+    if q.dtype not in (torch.bfloat16, torch.float32) or k.dtype != q.dtype or v.dtype != q.dtype:
+        return _delegate("dtype %s" % q.dtype, *args, **kw)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (q, k, v)):
+        return _delegate("autograd (the fused backward is not implemented yet)", *args, **kw)
+    B, H, Tq, D = q.shape
+    packed = _pack_reps(reps, f_dims, B)
+    if g("so3") and not g("se3"):
+        return _delegate("so3 without se3 (undefined in the reference as well, SURVEY T5)", *args, **kw)
+    if not g("se3") and not g("so3"):
+        packed.n_q_views = packed.n_k_views = 1
+    if Tq % packed.n_q_views or k.shape[2] % packed.n_k_views:
+        raise ValueError("token count must be divisible by the number of views")
+    tau = kwargs.get("tau", 1.0)
+    scale = float(getattr(attn_fn, "scale", D ** -0.5)) / float(tau)
+    tc = None
+    if g("se3"):
+        tc = trans_coeff if torch.is_tensor(trans_coeff) else torch.tensor([float(trans_coeff)], device=q.device)
+    out = ops.gta_attention_fwd(q, k, v, packed, f_dims, trans_coeff=tc, scale=scale, v_transform=v_transform)
+    return out, None
+
+
+def install(layers_module=None, gta_module=None):
+    """Rebind the reference's module globals to the fused op (source/layers.py:6,419 resolves the name at call
+    time).  Returns the original function."""
+    global _original
+    import importlib
+    layers_module = layers_module or importlib.import_module("source.layers")
+    gta_module = gta_module or importlib.import_module("source.utils.gta")
+    if _original is None:
+        _original = gta_module.multihead_geometric_transform_attention
+    layers_module.multihead_geometric_transform_attention = multihead_geometric_transform_attention
+    gta_module.multihead_geometric_transform_attention = multihead_geometric_transform_attention
+    return _original
+
+
+def uninstall(layers_module=None, gta_module=None):
+    global _original
+    import importlib
+    if _original is None:
+        return
+    layers_module = layers_module or importlib.import_module("source.layers")
+    gta_module = gta_module or importlib.import_module("source.utils.gta")
+    layers_module.multihead_geometric_transform_attention = _original
+    gta_module.multihead_geometric_transform_attention = _original
+    _original = None

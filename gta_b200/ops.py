@@ -1,0 +1,181 @@
+"""torch-facing wrappers over the C ABI: device memory, streams and strides come from torch, everything
+else is the CUDA library.  All tensors must live on a CUDA device."""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import GtaAttnParams, GtaReps, check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+@dataclasses.dataclass
+class PackedReps:
+    """Packed fp32 rep tables on the device (layout documented at GtaReps in include/gta_b200.h)."""
+    se3_q: Optional[torch.Tensor] = None   # [B,Nq,16]  E_q (unscaled)
+    se3_k: Optional[torch.Tensor] = None   # [B,Nk,16]  inv(E_k)
+    so3_q: Optional[torch.Tensor] = None   # [B,Nq,34]
+    so3_k: Optional[torch.Tensor] = None
+    so2_q: Optional[torch.Tensor] = None   # [B,Tq,C,2]
+    so2_k: Optional[torch.Tensor] = None
+    n_q_views: int = 1
+    n_k_views: int = 1
+
+    def c_struct(self) -> GtaReps:
+        return GtaReps(*[_ptr(getattr(self, n)) for n in ("se3_q", "se3_k", "so3_q", "so3_k", "so2_q", "so2_k")])
+
+
+def build_reps(extr_q: torch.Tensor, extr_k: torch.Tensor, coord_q: torch.Tensor, coord_k: torch.Tensor, *,
+               so2_nfreqs: int, so3_maxdeg: int, max_freq_h: float = 1.0, max_freq_w: float = 1.0,
+               shared_freqs: bool = False, se3: bool = True) -> PackedReps:
+    """Device-side pre_compute_reps (reference: source/encoder.py:183-265, source/decoder.py:247-353).
+    extr_* [B,N,4,4], coord_* [B,T,2] (or [B,N,t,2])."""
+    dev = extr_k.device
+    assert dev.type == "cuda", "gta_b200 runs on CUDA devices only"
+    eq, ek = _f32c(extr_q), _f32c(extr_k)
+    B, Nq, Nk = eq.shape[0], eq.shape[1], ek.shape[1]
+    cq = _f32c(coord_q).reshape(B, -1, 2)
+    ck = _f32c(coord_k).reshape(B, -1, 2)
+    Tq, Tk = cq.shape[1], ck.shape[1]
+    same = (extr_q is extr_k) and (coord_q is coord_k)
+    f = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    r = PackedReps(n_q_views=Nq, n_k_views=Nk)
+    if se3 or so3_maxdeg:
+        r.se3_q, r.se3_k = f(B, Nq, 16), f(B, Nk, 16)
+    if so3_maxdeg:
+        r.so3_q, r.so3_k = f(B, Nq, 34), f(B, Nk, 34)
+    if so2_nfreqs:
+        r.so2_k = f(B, Tk, 2 * so2_nfreqs, 2)
+        r.so2_q = r.so2_k if same else f(B, Tq, 2 * so2_nfreqs, 2)
+    check(lib().gta_build_reps(_ptr(eq), _ptr(ek), _ptr(cq), _ptr(ck), B, Nq, Nk, Tq, Tk, int(so2_nfreqs),
+                               float(max_freq_h), float(max_freq_w), int(shared_freqs), int(so3_maxdeg),
+                               _ptr(r.se3_q), _ptr(r.se3_k), _ptr(r.so3_q), _ptr(r.so3_k), _ptr(r.so2_q),
+                               _ptr(r.so2_k), _stream()), "gta_build_reps")
+    return r
+
+
+_DT = {torch.bfloat16: _lib.GTA_DTYPE_BF16, torch.float32: _lib.GTA_DTYPE_F32}
+_ws_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def _workspace(dev, nbytes: int) -> torch.Tensor:
+    key = (dev.index,)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes + 1024, device=dev, dtype=torch.uint8)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _params(q, k, v, out, reps: PackedReps, f_dims, trans_coeff, scale, v_transform, flags, lse=None):
+    assert q.is_cuda and k.is_cuda and v.is_cuda, "gta_b200 runs on CUDA devices only"
+    assert q.dtype == k.dtype == v.dtype and q.dtype in _DT, "q/k/v must all be bf16 or all fp32"
+    B, H, Tq, D = q.shape
+    Tk = k.shape[2]
+    for t in (q, k, v):
+        assert t.stride(3) == 1, "head dim must be contiguous"
+    g = lambda n: int(f_dims.get(n, 0) or 0)
+    p = GtaAttnParams()
+    p.q, p.k, p.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    p.q_stride_b, p.q_stride_h, p.q_stride_t = q.stride(0), q.stride(1), q.stride(2)
+    p.k_stride_b, p.k_stride_h, p.k_stride_t = k.stride(0), k.stride(1), k.stride(2)
+    p.v_stride_b, p.v_stride_h, p.v_stride_t = v.stride(0), v.stride(1), v.stride(2)
+    p.out = _ptr(out)
+    p.lse = _ptr(lse)
+    p.B, p.H, p.Tq, p.Tk, p.D = B, H, Tq, Tk, D
+    p.Nq, p.Nk = reps.n_q_views, reps.n_k_views
+    p.triv, p.se3, p.so3, p.so2 = g("triv"), g("se3"), g("so3"), g("so2")
+    if g("t2"):
+        raise NotImplementedError("gta_b200: the t2 block is not implemented")
+    p.reps = reps.c_struct()
+    p.trans_coeff = _ptr(trans_coeff)
+    p.scale = float(scale)
+    p.in_dtype = _DT[q.dtype]
+    p.out_dtype = _DT[out.dtype] if out is not None else _DT[q.dtype]
+    p.v_transform = int(bool(v_transform))
+    p.flags = int(flags)
+    return p
+
+
+def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: PackedReps, f_dims: dict, *,
+                      trans_coeff: Optional[torch.Tensor] = None, scale: Optional[float] = None,
+                      v_transform: bool = True, out_dtype: Optional[torch.dtype] = None,
+                      return_lse: bool = False, flags: int = 0):
+    """q [B,H,Tq,D], k,v [B,H,Tk,D] (strided views allowed) -> out [B,H,Tq,D] as a permuted view of a
+    contiguous [B,Tq,H,D] buffer (so the reference's 'b h n d -> b n (h d)' is free)."""
+    B, H, Tq, D = q.shape
+    dev = q.device
+    if scale is None:
+        scale = D ** -0.5
+    if trans_coeff is not None:
+        trans_coeff = trans_coeff.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
+    out = torch.empty(B, Tq, H, D, device=dev, dtype=out_dtype or q.dtype)
+    lse = torch.empty(B, H, Tq, device=dev, dtype=torch.float32) if return_lse else None
+    p = _params(q, k, v, out, reps, f_dims, trans_coeff, scale, v_transform, flags, lse)
+    nbytes = lib().gta_attn_fwd_workspace_bytes(B, H, k.shape[2], D)
+    ws = _workspace(dev, nbytes)
+    base = ws.data_ptr()
+    p.workspace = (base + 1023) // 1024 * 1024
+    p.workspace_bytes = nbytes
+    check(lib().gta_attn_fwd(p, _stream()), "gta_attn_fwd")
+    res = out.permute(0, 2, 1, 3)
+    return (res, lse) if return_lse else res
+
+
+def rotate_debug(q, k, v, reps: PackedReps, f_dims: dict, *, trans_coeff=None, v_transform=True):
+    """fp32 rotated operands (q', k', v') as contiguous [B,H,T,D] tensors — for tests."""
+    dev = q.device
+    if trans_coeff is not None:
+        trans_coeff = trans_coeff.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
+    B, H, Tq, D = q.shape
+    Tk = k.shape[2]
+    qt = torch.empty(B, H, Tq, D, device=dev, dtype=torch.float32)
+    kt = torch.empty(B, H, Tk, D, device=dev, dtype=torch.float32)
+    vt = torch.empty(B, H, Tk, D, device=dev, dtype=torch.float32)
+    dummy = torch.empty(16, device=dev, dtype=q.dtype)
+    p = _params(q, k, v, dummy, reps, f_dims, trans_coeff, 1.0, v_transform, 0)
+    check(lib().gta_rotate_debug(p, _ptr(qt), _ptr(kt), _ptr(vt), _stream()), "gta_rotate_debug")
+    return qt, kt, vt
+
+
+def so2_mats(coord: torch.Tensor, nfreqs: int, max_freqs=(1, 1), shared_freqs: bool = False) -> torch.Tensor:
+    """[..., 2] -> [..., 2*nfreqs, 2, 2] (pair index = freq*2 + axis)."""
+    assert coord.is_cuda and coord.shape[-1] == 2
+    c = _f32c(coord).reshape(-1, 2)
+    out = torch.empty(c.shape[0], 2 * nfreqs, 2, 2, device=c.device, dtype=torch.float32)
+    check(lib().gta_so2_mats(_ptr(c), c.shape[0], int(nfreqs), float(max_freqs[0]), float(max_freqs[1]),
+                             int(shared_freqs), _ptr(out), _stream()), "gta_so2_mats")
+    return out.reshape(*coord.shape[:-1], 2 * nfreqs, 2, 2)
+
+
+def wigner_d(R: torch.Tensor):
+    """R [n,3,3] -> (D1 [n,3,3], D2 [n,5,5])."""
+    assert R.is_cuda and R.shape[-2:] == (3, 3)
+    r = _f32c(R).reshape(-1, 3, 3)
+    d1 = torch.empty(r.shape[0], 3, 3, device=r.device, dtype=torch.float32)
+    d2 = torch.empty(r.shape[0], 5, 5, device=r.device, dtype=torch.float32)
+    check(lib().gta_wigner_d(_ptr(r), r.shape[0], _ptr(d1), _ptr(d2), _stream()), "gta_wigner_d")
+    return d1, d2
+
+
+def umma_probe(A, Bm, P, V, p_in_tmem: bool):
+    D = A.shape[1]
+    outS = torch.empty(128, 128, device=A.device, dtype=torch.float32)
+    outO = torch.empty(128, D, device=A.device, dtype=torch.float32)
+    check(lib().gta_umma_probe(_ptr(A), _ptr(Bm), _ptr(P), _ptr(V), D, int(p_in_tmem), _ptr(outS), _ptr(outO),
+                               _stream()), "gta_umma_probe")
+    return outS, outO

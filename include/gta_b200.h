@@ -1,0 +1,118 @@
+/*
+ * gta_b200 — C ABI of the B200-native geometric-transform-attention (GTA) path.
+ *
+ * Drop-in boundary for the hot path of autonomousvision/gta (paths relative to the reference root):
+ *   gta_attn_fwd          replaces  multihead_geometric_transform_attention  source/utils/gta.py:92-279
+ *                         together with AttnFn.forward                         source/layers.py:202-211
+ *                         (sole call site: Attention.forward, source/layers.py:422-428)
+ *   gta_build_reps        replaces  ImprovedSRTEncoder/Decoder.pre_compute_reps source/encoder.py:183-265,
+ *                                                                              source/decoder.py:247-353
+ *   gta_so2_mats          replaces  make_SO2mats                               source/utils/gta.py:47-69
+ *   gta_wigner_d          replaces  rotmat_to_wigner_d_matrices (l = 1, 2)     source/utils/wigner_d.py:52-58
+ *
+ * Conventions: plain pointers and sizes, no torch types.  All pointers are DEVICE pointers unless
+ * noted; `stream` is a cudaStream_t passed as void*.  Every entry point returns 0 on success or a
+ * negative GTA_ERR_* code and never throws; gta_last_error() returns a thread-local message.
+ * No ownership is transferred: the caller allocates every buffer (sizes below / gta_attn_fwd_workspace_bytes).
+ */
+#ifndef GTA_B200_H_
+#define GTA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTA_OK 0
+#define GTA_ERR_INVALID (-1)      /* bad argument / unsupported shape */
+#define GTA_ERR_CUDA (-2)         /* CUDA runtime error (message has the cudaError string) */
+#define GTA_ERR_UNSUPPORTED (-3)  /* valid in the reference but not implemented here (t2, euclid, ...) */
+
+#define GTA_DTYPE_BF16 0
+#define GTA_DTYPE_F32 1
+
+/* Packed rep tables (fp32), produced by gta_build_reps or packed from the reference's `extras`:
+ *   se3_q [B,Nq,16]  E_q row-major, UNSCALED (= extras['inv_se3rep_q']); the kernels apply
+ *                    scale_mask(trans_coeff) on load                      (source/utils/gta.py:135-141)
+ *   se3_k [B,Nk,16]  inv(E_k) row-major, unscaled (= extras['se3rep_k'])
+ *   so3_q [B,Nq,34]  Wigner D_1 (9) | D_2 (25) of inv(E_q)[:3,:3]  (= extras['so3rep_q'])
+ *   so3_k [B,Nk,34]
+ *   so2_q [B,Tq,C,2] (cos, sin) of theta[t, j*2+axis], C = 2*nfreqs (= extras['so2rep_q'][...,0,0] / [...,1,0])
+ *   so2_k [B,Tk,C,2]
+ * Pointers of absent blocks may be NULL. */
+typedef struct GtaReps {
+    const float* se3_q;
+    const float* se3_k;
+    const float* so3_q;
+    const float* so3_k;
+    const float* so2_q;
+    const float* so2_k;
+} GtaReps;
+
+typedef struct GtaAttnParams {
+    /* q [B,H,Tq,D], k,v [B,H,Tk,D]: arbitrary batch/head/token strides (in ELEMENTS), unit stride in D.
+     * These are the strided views the reference passes (source/layers.py:394-395). */
+    const void* q;
+    const void* k;
+    const void* v;
+    int64_t q_stride_b, q_stride_h, q_stride_t;
+    int64_t k_stride_b, k_stride_h, k_stride_t;
+    int64_t v_stride_b, v_stride_h, v_stride_t;
+    /* out [B,Tq,H,D] contiguous (so 'b h n d -> b n (h d)' at layers.py:429 is a free view). */
+    void* out;
+    float* lse; /* optional [B,H,Tq] natural-log-sum-exp of the scaled logits; may be NULL */
+    int B, H, Tq, Tk, D;
+    int Nq, Nk;                /* views; token t belongs to view t / (T/N)  (gta.py:160-162) */
+    int triv, se3, so3, so2;   /* f_dims, fixed order triv|se3|so3|so2 (gta.py:115) */
+    GtaReps reps;
+    const float* trans_coeff;  /* DEVICE pointer to the layer's scalar parameter (layers.py:188-191); NULL => 1.0 */
+    float scale;               /* attn_fn.scale / tau  (layers.py:209) */
+    int in_dtype, out_dtype;   /* GTA_DTYPE_* */
+    int v_transform;           /* gta.py:156,168,277 */
+    void* workspace;           /* >= gta_attn_fwd_workspace_bytes(...) bytes, 1024-byte aligned */
+    size_t workspace_bytes;
+    int flags;                 /* GTA_FLAG_* */
+} GtaAttnParams;
+
+#define GTA_FLAG_P_IN_TMEM 1   /* P operand of the PV MMA read from tensor memory instead of shared memory */
+#define GTA_FLAG_SKIP_STAGE 2  /* workspace already holds K'/V' of these inputs: launch only the attention kernel */
+#define GTA_FLAG_STAGE_ONLY 4  /* launch only the K'/V' staging kernel (fills the workspace) */
+
+/* Scratch for the rotated K'/V' operand tiles. */
+size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D);
+
+/* Fused forward: O = rho_q^{-1} softmax((rho_q^{-T} Q)(rho_k K)^T * scale) (rho_k V). */
+int gta_attn_fwd(const GtaAttnParams* p, void* stream);
+
+/* Rotated operands only (q' = rho_q^{-T} q etc.), fp32 [B,H,T,D] contiguous; testing / inspection. */
+int gta_rotate_debug(const GtaAttnParams* p, float* qt, float* kt, float* vt, void* stream);
+
+/* extrinsics [B,N,4,4] fp32 row-major, coords [B,T,2] fp32 -> packed tables (see GtaReps).
+ * so3_maxdeg: 0 (skip) or 2.  Output pointers of skipped blocks may be NULL. */
+int gta_build_reps(const float* extr_q, const float* extr_k, const float* coord_q, const float* coord_k,
+                   int B, int Nq, int Nk, int Tq, int Tk, int so2_nfreqs, float max_freq_h, float max_freq_w,
+                   int shared_freqs, int so3_maxdeg, float* se3_q, float* se3_k, float* so3_q, float* so3_k,
+                   float* so2_q, float* so2_k, void* stream);
+
+/* coord [n,2] -> mats [n, 2*nfreqs, 2, 2] in the reference's layout (freq-major, axis-minor pairs). */
+int gta_so2_mats(const float* coord, int64_t n, int nfreqs, float max_freq_h, float max_freq_w, int shared_freqs,
+                 float* mats, void* stream);
+
+/* R [n,3,3] -> d1 [n,3,3], d2 [n,5,5] (ZYZ Euler angles with gimbal handling, D_l = Z J Z J Z). */
+int gta_wigner_d(const float* R, int64_t n, float* d1, float* d2, void* stream);
+
+/* tcgen05 self-test used by tests/test_umma_probe.py: S = A B^T (A,B [128,D] bf16 row-major) and
+ * O = P V (P [128,128] bf16, V [128,D] bf16) through the same descriptor helpers as gta_attn_fwd.
+ * outS [128,128], outO [128,D] fp32.  p_in_tmem selects the TS form for the PV product. */
+int gta_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem,
+                   float* outS, float* outO, void* stream);
+
+const char* gta_last_error(void);
+int gta_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTA_B200_H_ */

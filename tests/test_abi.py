@@ -1,0 +1,97 @@
+"""CPU tests of the C-ABI boundary: the library builds/loads, exports every symbol include/gta_b200.h declares,
+and validates its arguments (no CUDA work is launched here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from gta_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "gta_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gta_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree():
+    decl = _declared_symbols()
+    assert decl, "no declarations parsed"
+    assert sorted(_lib.SYMBOLS) == decl
+
+
+def test_library_exports_every_declared_symbol():
+    l = _lib.lib()
+    for name in _declared_symbols():
+        assert hasattr(l, name), name
+    assert l.gta_abi_version() == 1
+
+
+def test_struct_layout_matches_header_order():
+    names = [f[0] for f in _lib.GtaAttnParams._fields_]
+    txt = open(os.path.join(ROOT, "include", "gta_b200.h")).read()
+    body = txt[txt.index("typedef struct GtaAttnParams"):txt.index("} GtaAttnParams;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    order = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(void|float|int64_t|int|size_t|GtaReps)\s*\*?\s*", "", decl)
+        order += [d.strip().lstrip("*") for d in decl.split(",")]
+    assert order == names
+
+
+def test_workspace_bytes():
+    l = _lib.lib()
+    # 2 tensors x B*H x ceil(Tk/128) tiles x 128*D*2 bytes
+    assert l.gta_attn_fwd_workspace_bytes(2, 8, 1280, 96) == 2 * 2 * 8 * 10 * 128 * 96 * 2
+    assert l.gta_attn_fwd_workspace_bytes(1, 6, 600, 64) == 2 * 6 * 5 * 128 * 64 * 2
+    assert l.gta_attn_fwd_workspace_bytes(0, 6, 600, 64) == 0
+
+
+def _params(**over):
+    p = _lib.GtaAttnParams()
+    dummy = 0x1000
+    p.q = p.k = p.v = p.out = dummy
+    p.B, p.H, p.Tq, p.Tk, p.D = 1, 2, 16, 16, 32
+    p.Nq = p.Nk = 2
+    p.triv, p.se3, p.so3, p.so2 = 0, 16, 8, 8
+    p.reps = _lib.GtaReps(dummy, dummy, dummy, dummy, dummy, dummy)
+    p.q_stride_b = p.k_stride_b = p.v_stride_b = 16 * 2 * 32
+    p.q_stride_h = p.k_stride_h = p.v_stride_h = 32
+    p.q_stride_t = p.k_stride_t = p.v_stride_t = 64
+    p.scale = 1.0
+    p.v_transform = 1
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+@pytest.mark.parametrize("over,code,msg", [
+    (dict(D=48), -3, "head dim"),
+    (dict(se3=20, so3=4), -3, "multiple of 8"),
+    (dict(se3=24), -1, "sum to head dim"),
+    (dict(Tq=15), -1, "divisible"),
+    (dict(q=None), -1, "null"),
+    (dict(in_dtype=7), -3, "dtype"),
+    (dict(q_stride_t=65), -3, "16-byte"),
+    (dict(workspace=None), -1, "workspace"),
+])
+def test_argument_validation(over, code, msg):
+    l = _lib.lib()
+    p = _params(**over)
+    rc = l.gta_attn_fwd(ctypes.byref(p), None)
+    assert rc == code
+    assert msg in l.gta_last_error().decode()
+    assert l.gta_attn_fwd(None, None) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.GtaError, match="no CPU fallback"):
+        _lib.lib()

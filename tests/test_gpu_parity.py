@@ -1,0 +1,241 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs, against the committed golden vectors of the unmodified reference, and — at full benchmark
+sizes — through size-independent properties (frame invariance, linearity in V, identity-pose == plain softmax).
+
+Tolerances (BASELINE.json north_star): 1e-2 max-abs for the bf16 tensor-core path on N(0,1) inputs with the
+configured trans_coeff = 0.01; for trans_coeff = 1 the output-side SE(3) transform scales |out| by the translation
+magnitudes, so the bound is taken relative to max(1, |ref|_max)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gta_b200.synth import CFG1_A, CFG1_B, CLEVR, MSN_SO3, GtaConfig, make_inputs
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+BF16_TOL = 1e-2
+
+
+def _ops():
+    from gta_b200 import ops
+    return ops
+
+
+def _dev_reps(cfg, inp):
+    ops = _ops()
+    ek, ck = inp["extr_k"].cuda(), inp["coord_k"].cuda()
+    eq = ek if inp["extr_q"] is inp["extr_k"] else inp["extr_q"].cuda()
+    cq = ck if inp["coord_q"] is inp["coord_k"] else inp["coord_q"].cuda()
+    return ops.build_reps(eq, ek, cq, ck, so2_nfreqs=cfg.so2, so3_maxdeg=cfg.so3, max_freq_h=cfg.max_freq_h,
+                          max_freq_w=cfg.max_freq_w, shared_freqs=cfg.shared_freqs)
+
+
+def _run(cfg, inp, tc=0.01, flags=0, out_dtype=None):
+    ops = _ops()
+    reps = _dev_reps(cfg, inp)
+    out = ops.gta_attention_fwd(inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), reps, cfg.f_dims,
+                                trans_coeff=torch.tensor([tc], device="cuda"), v_transform=cfg.v_transform,
+                                flags=flags, out_dtype=out_dtype)
+    torch.cuda.synchronize()
+    return out.float().cpu().numpy()
+
+
+def _oracle(cfg, inp, tc=0.01):
+    from oracle import c_oracle
+    return c_oracle.gta_attention(cfg, inp["q"].float(), inp["k"].float(), inp["v"].float(), inp["extr_q"],
+                                  inp["extr_k"], inp["coord_q"], inp["coord_k"], trans_coeff=tc)
+
+
+def _tol(ref):
+    return BF16_TOL * max(1.0, float(np.abs(ref).max()))
+
+
+def test_umma_probe_exact():
+    """tcgen05 descriptors / tile images: S = A B^T and O = P V are exact in fp32 accumulation."""
+    ops = _ops()
+    torch.manual_seed(0)
+    for D in (32, 64, 96, 128):
+        A = torch.randn(128, D, device="cuda").bfloat16(); Bm = torch.randn(128, D, device="cuda").bfloat16()
+        P = torch.rand(128, 128, device="cuda").bfloat16(); V = torch.randn(128, D, device="cuda").bfloat16()
+        for tm in (False, True):
+            S, O = ops.umma_probe(A, Bm, P, V, tm)
+            assert (S - A.float() @ Bm.float().T).abs().max() < 1e-4
+            assert (O - P.float() @ V.float()).abs().max() < 1e-4
+
+
+def test_build_reps_matches_oracle():
+    from oracle import c_oracle
+    cfg = GtaConfig(**MSN_SO3, n_q_views=3, n_k_views=5)
+    inp = make_inputs(cfg, 2, 16, 64, cross=True, seed=1)
+    r = _dev_reps(cfg, inp)
+    o = c_oracle.build_reps(cfg, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"])
+    for k in ("se3_q", "se3_k", "so3_q", "so3_k", "so2_q", "so2_k"):
+        assert np.abs(getattr(r, k).cpu().numpy() - o[k]).max() < 2e-6, k
+
+
+def test_reps_golden_gimbal():
+    ops = _ops()
+    g = np.load(os.path.join(GOLDEN, "reps_gimbal.npz"))
+    E = torch.from_numpy(g["extr"]).cuda()
+    c = torch.from_numpy(g["coord"]).cuda()
+    r = ops.build_reps(E, E, c, c, so2_nfreqs=6, so3_maxdeg=2)
+    assert np.abs(r.so3_k[0, :, :9].reshape(5, 3, 3).cpu().numpy() - g["d1"]).max() < 2e-6
+    assert np.abs(r.so3_k[0, :, 9:].reshape(5, 5, 5).cpu().numpy() - g["d2"]).max() < 2e-6
+    assert np.abs(r.se3_k.reshape(1, 5, 4, 4).cpu().numpy() - g["inv"]).max() < 1e-6
+    from gta_b200 import gta as fast, wigner_d as fw
+    m = fast.make_SO2mats(c, 6).flatten(-4, -3)
+    assert np.abs(m.cpu().numpy() - g["so2_n6"]).max() < 2e-6
+    m = fast.make_SO2mats(c, 3, [2, 0.5], shared_freqs=True).flatten(-4, -3)
+    assert np.abs(m.cpu().numpy() - g["so2_n3_shared_f2_05"]).max() < 2e-6
+    R = torch.linalg.inv(torch.from_numpy(g["extr"]))[..., :3, :3].flatten(0, 1).cuda()
+    D = fw.rotmat_to_wigner_d_matrices(2, R)
+    assert np.abs(D[0].cpu().numpy() - g["d0"]).max() == 0
+    assert np.abs(D[1].cpu().numpy() - g["d1"]).max() < 2e-6
+    assert np.abs(D[2].cpu().numpy() - g["d2"]).max() < 2e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_rotated_operands_match_oracle(dtype):
+    from oracle import c_oracle
+    ops = _ops()
+    cfg = GtaConfig(**MSN_SO3, n_q_views=3, n_k_views=2)
+    inp = make_inputs(cfg, 2, 8, 16, cross=True, seed=2, dtype=dtype)
+    reps = _dev_reps(cfg, inp)
+    qt, kt, vt = ops.rotate_debug(inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), reps, cfg.f_dims,
+                                  trans_coeff=torch.tensor([0.3], device="cuda"))
+    _, q2, k2, v2 = c_oracle.gta_attention(cfg, inp["q"].float(), inp["k"].float(), inp["v"].float(), inp["extr_q"],
+                                           inp["extr_k"], inp["coord_q"], inp["coord_k"], trans_coeff=0.3,
+                                           return_rotated=True)
+    for a, b in ((qt, q2), (kt, k2), (vt, v2)):
+        assert np.abs(a.cpu().numpy() - b).max() < 5e-6
+
+
+@pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                                        if "reps_" not in p))
+@pytest.mark.parametrize("flags", [0, 1])
+def test_golden_vectors(name, flags):
+    """Committed outputs of the unmodified reference (fp32, CPU) vs the fused kernel fed the same fp32 inputs."""
+    from tests.golden.gen_golden import CASES
+    case = [c for c in CASES if c[0] == name][0]
+    _, base, nq, nk, tq, tk, cross, B, tc, seed, vt = case
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk, v_transform=vt)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    inp = {k: torch.from_numpy(g[k]) for k in ("q", "k", "v", "extr_q", "extr_k", "coord_q", "coord_k")}
+    if not cross:
+        inp["extr_q"], inp["coord_q"] = inp["extr_k"], inp["coord_k"]
+    out = _run(cfg, inp, tc=float(g["trans_coeff"]), flags=flags)
+    assert np.abs(out - g["out"]).max() < _tol(g["out"])
+
+
+CASES_GPU = [
+    # base, Nq, Nk, tq, tk, cross, B, dtype, tc
+    (CFG1_A, 2, 2, 64, 64, False, 1, torch.bfloat16, 0.01),       # exactly one key tile
+    (CFG1_B, 2, 2, 16, 16, False, 2, torch.float32, 0.01),        # a single partial tile
+    (CFG1_B, 1, 1, 1, 1, False, 1, torch.bfloat16, 0.01),         # one token
+    (CFG1_A, 2, 2, 1024, 1024, False, 2, torch.bfloat16, 0.01),   # BASELINE config 1 shape (T=2048)
+    (MSN_SO3, 5, 5, 64, 64, False, 1, torch.bfloat16, 0.01),      # 3 tiles, tail 64
+    (MSN_SO3, 5, 5, 256, 256, False, 2, torch.bfloat16, 0.01),    # MSN encoder shape
+    (MSN_SO3, 5, 5, 512, 256, True, 1, torch.bfloat16, 0.01),     # MSN decoder shape
+    (CLEVR, 2, 2, 300, 300, False, 2, torch.bfloat16, 0.01),      # CLEVR encoder shape (views straddle tiles)
+    (CLEVR, 3, 2, 853, 300, True, 1, torch.bfloat16, 0.01),       # CLEVR decoder shape (Tq=2559)
+    (CLEVR, 3, 2, 853, 300, True, 1, torch.float32, 1.0),         # fp32 I/O, trans_coeff 1
+    (MSN_SO3, 1, 5, 1, 256, True, 2, torch.bfloat16, 0.01),       # render path: one query token
+]
+
+
+@pytest.mark.parametrize("case", CASES_GPU, ids=lambda c: f"D{c[0]['head_dim']}_{c[1]}x{c[3]}_{c[2]}x{c[4]}_{'x' if c[5] else 's'}_{str(c[7])[6:]}")
+@pytest.mark.parametrize("flags", [0, 1], ids=["P_smem", "P_tmem"])
+def test_fused_attention_matches_oracle(case, flags):
+    base, nq, nk, tq, tk, cross, B, dtype, tc = case
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
+    inp = make_inputs(cfg, B, tq, tk, cross=cross, seed=7, dtype=dtype)
+    ref = _oracle(cfg, inp, tc)
+    out = _run(cfg, inp, tc, flags)
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() < _tol(ref)
+
+
+def test_contiguous_and_strided_inputs_agree():
+    cfg = GtaConfig(**MSN_SO3, n_q_views=2, n_k_views=2)
+    a = make_inputs(cfg, 2, 100, 100, cross=False, seed=3, dtype=torch.bfloat16, packed_layout=True)
+    b = make_inputs(cfg, 2, 100, 100, cross=False, seed=3, dtype=torch.bfloat16, packed_layout=False)
+    assert not a["q"].is_contiguous() and b["q"].is_contiguous()
+    assert np.array_equal(_run(cfg, a), _run(cfg, b))
+
+
+def test_v_transform_false_and_lse():
+    ops = _ops()
+    cfg = GtaConfig(**CLEVR, n_q_views=3, n_k_views=2, v_transform=False)
+    inp = make_inputs(cfg, 1, 50, 70, cross=True, seed=4, dtype=torch.bfloat16)
+    ref = _oracle(cfg, inp)
+    out = _run(cfg, inp)
+    assert np.abs(out - ref).max() < _tol(ref)
+    reps = _dev_reps(cfg, inp)
+    o2, lse = ops.gta_attention_fwd(inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), reps, cfg.f_dims,
+                                    trans_coeff=torch.tensor([0.01], device="cuda"), v_transform=False, return_lse=True)
+    from oracle import torch_port as tp
+    r = tp.build_reps(cfg, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"])
+    qt, kt, _ = tp.transform_qkv(cfg, inp["q"].float(), inp["k"].float(), inp["v"].float(), r, 0.01)
+    lse_ref = torch.logsumexp(qt @ kt.transpose(-1, -2) * cfg.head_dim ** -0.5, -1)
+    assert (lse.cpu() - lse_ref).abs().max() < 5e-2
+
+
+def test_identity_pose_is_plain_attention_full_size():
+    """Size-independent property at the MSN benchmark shape: identity extrinsics + zero coords => softmax(QK^T)V."""
+    cfg = GtaConfig(**MSN_SO3, n_q_views=5, n_k_views=5)
+    inp = make_inputs(cfg, 4, 256, 256, cross=False, seed=5, dtype=torch.bfloat16)
+    inp["extr_q"] = inp["extr_k"] = torch.eye(4).expand(4, 5, 4, 4).contiguous()
+    inp["coord_q"] = inp["coord_k"] = torch.zeros(4, 1280, 2)
+    out = _run(cfg, inp)
+    q, k, v = (inp[n].cuda().float() for n in "qkv")
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).cpu().numpy()
+    assert np.abs(out - ref).max() < BF16_TOL
+
+
+def test_frame_invariance_and_linearity_full_size():
+    """E_i -> E_i G for one global SE(3) G leaves the output unchanged; the op is linear in V."""
+    from gta_b200.synth import random_extrinsics
+    cfg = GtaConfig(**MSN_SO3, n_q_views=5, n_k_views=5)
+    inp = make_inputs(cfg, 2, 256, 256, cross=False, seed=6, dtype=torch.bfloat16)
+    base = _run(cfg, inp, out_dtype=torch.float32)
+    G = random_extrinsics(torch.Generator().manual_seed(1), 1, 1, False)[0, 0].double()
+    inp2 = dict(inp)
+    inp2["extr_q"] = inp2["extr_k"] = (inp["extr_k"].double() @ G).float()
+    assert np.abs(_run(cfg, inp2, out_dtype=torch.float32) - base).max() < BF16_TOL
+    inp3 = dict(inp)
+    inp3["v"] = (inp["v"].float() * 2).to(torch.bfloat16)      # exact in bf16
+    assert np.abs(_run(cfg, inp3, out_dtype=torch.float32) - 2 * base).max() < 1e-5
+
+
+def test_dropin_signature_with_reference_format_reps():
+    """multihead_geometric_transform_attention(q,k,v,attn_fn,f_dims,reps,...) fed rep tensors laid out as the
+    reference's pre_compute_reps leaves them in `extras`."""
+    from gta_b200 import gta as fast
+    from oracle import torch_port as tp
+    cfg = GtaConfig(**MSN_SO3, n_q_views=3, n_k_views=2)
+    inp = make_inputs(cfg, 2, 40, 64, cross=True, seed=8, dtype=torch.bfloat16)
+    r = tp.build_reps(cfg, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"])
+    extras = {
+        "se3rep_q": torch.linalg.inv(inp["extr_q"]).cuda(), "se3rep_k": r["se3_k"].cuda(),
+        "inv_se3rep_q": r["se3_qinv"].cuda(),
+        "so3rep_q": [r["so3_d1_q"].cuda(), r["so3_d2_q"].cuda()], "so3rep_k": [r["so3_d1_k"].cuda(), r["so3_d2_k"].cuda()],
+        "so2rep_q": tp.so2_mats(r["so2_th_q"]).cuda(), "so2rep_k": tp.so2_mats(r["so2_th_k"]).cuda(),
+    }
+
+    class AttnFn:
+        scale = cfg.head_dim ** -0.5
+    tc = torch.nn.Parameter(torch.tensor([0.01], device="cuda"))
+    with torch.no_grad():
+        out, attn = fast.multihead_geometric_transform_attention(
+            inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), attn_fn=AttnFn(), f_dims=cfg.f_dims, reps=extras,
+            trans_coeff=tc, v_transform=True, euclid=False)
+    assert attn is None and out.shape == inp["q"].shape
+    ref = _oracle(cfg, inp)
+    assert np.abs(out.float().cpu().numpy() - ref).max() < _tol(ref)
+    assert "_gta_b200_packed" in extras      # packed once, reused by the next layer
+    with pytest.raises(NotImplementedError):
+        fast.multihead_geometric_transform_attention(inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), AttnFn(),
+                                                     cfg.f_dims, extras, trans_coeff=tc, euclid=True)
