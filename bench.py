@@ -1,0 +1,376 @@
+"""Benchmark of the GTA-attention hot path (BASELINE.json metric: GTA-attention Mtokens/s at the MSN-Hard
+gta_so3 token shape; one process per GPU, batch-sharded, no collective in the forward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload msn_enc|msn_dec|clevr_enc|clevr_dec|cfg1]
+    python bench.py --impl reference ...     # the reference's CPU path (torch restatement) on the host cores
+
+A step = one pass of the hot path over one batch of synthetic input: rep construction (once per batch, as the
+reference does per encoder forward) + K'/V' staging + the fused attention kernel.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from gta_b200.synth import CFG1_A, CLEVR, MSN_SO3, GtaConfig, make_inputs  # noqa: E402
+
+WORKLOADS = {
+    # name: (base cfg, Nq, Nk, tq/view, tk/view, cross, per-GPU batch, description)
+    "msn_enc": (MSN_SO3, 5, 5, 256, 256, False, 64, "runs/msn/GTA/gta_so3 encoder self-attention, 5 views x 16x16 tokens"),
+    "msn_dec": (MSN_SO3, 5, 5, 512, 256, True, 64, "runs/msn/GTA/gta_so3 decoder cross-attention, Tq=2560, Tk=1280"),
+    "clevr_enc": (CLEVR, 2, 2, 300, 300, False, 32, "runs/clevrtr/GTA/gta encoder self-attention, 2 views x 15x20 tokens"),
+    "clevr_dec": (CLEVR, 3, 2, 853, 300, True, 32, "runs/clevrtr/GTA/gta decoder cross-attention, Tq=2559, Tk=600"),
+    "cfg1": (CFG1_A, 2, 2, 1024, 1024, False, 2, "BASELINE config 1: 2 views x 32x32, d=128, 4 heads"),
+}
+METRIC = "GTA-attention Mtokens/sec"
+UNIT = "Mtokens/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons sampled DURING the timed region through NVML (in-process, ~2 ms period;
+    falls back to polling nvidia-smi when pynvml is unavailable)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.max_mhz = index, [], False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # NVML indices follow CUDA_VISIBLE_DEVICES only through the UUID; map via torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            self.handle = None
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(h)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    self.handle = h
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                if self.nvml is not None:
+                    mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+                    mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    self.samples.append((mhz, mask))
+                    time.sleep(0.002)
+                else:
+                    o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    f = [x.strip() for x in o.strip().split(",")]
+                    self.samples.append((float(f[0]), 0))
+                    self.max_mhz = float(f[1])
+            except Exception:
+                time.sleep(0.01)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        sm = sorted(s[0] for s in self.samples)
+        mask = 0
+        for s in self.samples:
+            mask |= s[1]
+        reasons = [n for bit, n in self.REASONS.items() if mask & bit]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_port_step(cfg, inp, tc=0.01):
+    """The reference's CPU path restated with the same ATen ops (oracle/torch_port.py), fp32."""
+    from oracle import torch_port as tp
+    return tp.gta_attention(cfg, inp["q"], inp["k"], inp["v"], inp["extr_q"], inp["extr_k"], inp["coord_q"],
+                            inp["coord_k"], trans_coeff=tc)
+
+
+def _best_threads(cfg, inp):
+    """torch's intra-op pool scales badly on the many small einsums of this path: try a few pool sizes and keep the
+    fastest (the count actually used is what `cores` reports)."""
+    ncpu = os.cpu_count() or 1
+    best = (float("inf"), 1)
+    for th in sorted({1, 4, 8, 16, 32, 64, ncpu}):
+        if th > ncpu:
+            continue
+        torch.set_num_threads(th)
+        cpu_port_step(cfg, inp)
+        t0 = time.perf_counter()
+        cpu_port_step(cfg, inp)
+        dt = time.perf_counter() - t0
+        if dt < best[0]:
+            best = (dt, th)
+    torch.set_num_threads(best[1])
+    return best[1]
+
+
+def cpu_baseline(cfg, args_w, budget_s=12.0, batch=2):
+    base, nq, nk, tq, tk, cross, _, _ = args_w
+    inp = make_inputs(cfg, batch, tq, tk, cross=cross, seed=123)
+    inp = {k: (v.contiguous() if k in "qkv" else v) for k, v in inp.items()}
+    with torch.no_grad():
+        threads = _best_threads(cfg, inp)
+        t0, reps = time.perf_counter(), 0
+        best = float("inf")
+        while reps < 3 or (time.perf_counter() - t0 < budget_s and reps < 50):
+            t1 = time.perf_counter()
+            cpu_port_step(cfg, inp)
+            best = min(best, time.perf_counter() - t1)
+            reps += 1
+    tokens = batch * nq * tq
+    return {"value": tokens / best / 1e6, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"oracle/torch_port.py (ATen restatement of the reference path), fp32, batch {batch} of the same "
+                      f"token shape, best of {reps}, {best*1e3:.1f} ms, thread count chosen as the fastest of a sweep"}
+
+
+def run_reference(args, wl):
+    base, nq, nk, tq, tk, cross, _, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
+    batch = 2
+    inp = make_inputs(cfg, batch, tq, tk, cross=cross, seed=123)
+    inp = {k: (v.contiguous() if k in "qkv" else v) for k, v in inp.items()}
+    with torch.no_grad():
+        threads = _best_threads(cfg, inp)
+        for _ in range(args.warmup):
+            cpu_port_step(cfg, inp)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_port_step(cfg, inp)
+        dt = (time.perf_counter() - t0) / args.steps
+    val = batch * nq * tq / dt / 1e6
+    sample = (f"oracle/torch_port.py: the reference's CPU path restated with the same ATen ops (the reference is "
+              f"pure Python and is not present on the GPU box), fp32, {threads} threads (fastest of a sweep; host has "
+              f"{os.cpu_count()} cpus), batch {batch} per step")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, wl, batch),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, wl, batch):
+    base, nq, nk, tq, tk, cross, _, desc = wl
+    return {"workload": name, "description": desc, "batch_per_gpu": batch, "heads": base["heads"],
+            "head_dim": base["head_dim"], "Tq": nq * tq, "Tk": nk * tk, "q_views": nq, "k_views": nk,
+            "f_dims": base["f_dims"], "attention": "cross" if cross else "self", "trans_coeff": 0.01,
+            "parallelism": "batch-shard, one process per GPU, no collective in the forward"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="msn_enc", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--flags", type=int, default=0, help="GTA_FLAG_* bits for gta_attn_fwd (1 = P in TMEM)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    base, nq, nk, tq, tk, cross, B, desc = wl
+    if args.batch:
+        B = args.batch
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gta_b200 import _lib, ops
+    _lib.lib()
+
+    # ---- synthetic inputs, pinned on the host (e2e leg) and resident on the device (value leg)
+    host = make_inputs(cfg, B, tq, tk, cross=cross, seed=1000 + rank, dtype=torch.bfloat16)
+    self_attn = not cross
+    pin = {}
+    for k_, v_ in host.items():
+        if self_attn and k_ in ("extr_q", "coord_q"):
+            continue
+        pin[k_] = v_
+    # q/k/v are views of shared projection buffers: keep the buffers pinned and re-derive the views
+    if self_attn:
+        buf = host["q"]._base if host["q"]._base is not None else host["q"]
+        while buf._base is not None:
+            buf = buf._base
+        bufs_host = {"qkv": buf.pin_memory()}
+    else:
+        bq, bkv = host["q"], host["k"]
+        while bq._base is not None:
+            bq = bq._base
+        while bkv._base is not None:
+            bkv = bkv._base
+        bufs_host = {"q": bq.pin_memory(), "kv": bkv.pin_memory()}
+    small_host = {k_: host[k_].contiguous().pin_memory() for k_ in ("extr_k", "coord_k")}
+    if cross:
+        small_host.update({k_: host[k_].contiguous().pin_memory() for k_ in ("extr_q", "coord_q")})
+    H, D = cfg.heads, cfg.head_dim
+
+    def views(bufs):
+        hv = lambda x: x.view(x.shape[0], x.shape[1], -1, D).permute(0, 2, 1, 3)
+        if self_attn:
+            q, k, v = (hv(t) for t in bufs["qkv"].chunk(3, dim=-1))
+        else:
+            q = hv(bufs["q"])
+            k, v = (hv(t) for t in bufs["kv"].chunk(2, dim=-1))
+        return q, k, v
+
+    dev_bufs = {k_: torch.empty_like(v_, device=dev) for k_, v_ in bufs_host.items()}
+    dev_small = {k_: torch.empty_like(v_, device=dev) for k_, v_ in small_host.items()}
+    out_host = torch.empty(B, nq * tq, H, D, dtype=torch.bfloat16).pin_memory()
+    tc = torch.tensor([0.01], device=dev)
+
+    def h2d():
+        for k_ in bufs_host:
+            dev_bufs[k_].copy_(bufs_host[k_], non_blocking=True)
+        for k_ in small_host:
+            dev_small[k_].copy_(small_host[k_], non_blocking=True)
+
+    def step(flags=0):
+        ek, ck = dev_small["extr_k"], dev_small["coord_k"]
+        eq = dev_small.get("extr_q", ek) if cross else ek
+        cq = dev_small.get("coord_q", ck) if cross else ck
+        reps = ops.build_reps(eq, ek, cq, ck, so2_nfreqs=cfg.so2, so3_maxdeg=cfg.so3)
+        q, k, v = views(dev_bufs)
+        return ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, flags=args.flags | flags), reps
+
+    h2d()
+    torch.cuda.synchronize()
+    in_bytes = sum(t.numel() * t.element_size() for t in dev_bufs.values())
+    launches_per_step = (1 if not cfg.dims()[1] and not cfg.so3 else 1) + (1 if cross else 1) + (1 if cross else 0) + 2
+    # build_view_reps (1) + so2 tables (1 self / 2 cross) + staging (1) + attention (1)
+    launches_per_step = 1 + (2 if cross else 1) + 2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms / n
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    sampler.start()
+    ms_step = timed(step, args.steps)
+    clocks = sampler.summary()
+
+    # ---- dominant kernel alone (K'/V' already staged in the workspace): roofline numerator
+    _, reps = step()
+    q, k, v = views(dev_bufs)
+    attn_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc,
+                                              flags=args.flags | _lib.GTA_FLAG_SKIP_STAGE)
+    stage_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc,
+                                               flags=args.flags | _lib.GTA_FLAG_STAGE_ONLY)
+    for _ in range(3):
+        attn_only()
+    ms_attn = timed(attn_only, args.steps)
+    ms_stage = timed(stage_only, args.steps)
+
+    # ---- end to end through the public API with pinned HOST buffers
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            h2d()
+            o, _ = step()
+            out_host.copy_(o.permute(0, 2, 1, 3), non_blocking=True)
+        for _ in range(2):
+            e2e_step()
+        n_e2e = max(3, args.steps // 2)
+        ms_e2e = timed(e2e_step, n_e2e)
+        h2d_bytes = in_bytes + sum(t.numel() * t.element_size() for t in dev_small.values())
+        e2e = {"value": world * B * nq * tq / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e, "steps": n_e2e}
+
+    if rank == 0:
+        Tq, Tk = nq * tq, nk * tk
+        flops = 4.0 * B * H * Tq * Tk * D
+        pk, pk_src = peaks()
+        total_s = ms_step * 1e-3 * args.steps
+        peak = pk["bf16_tflops"] if total_s < 2.0 else pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        achieved = flops / (ms_attn * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": world * B * Tq / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": dict(workload_config(args.workload, wl, B),
+                           l2="q/k/v inputs %.0f MB per step > 126 MB L2 (no explicit flush needed)" % (in_bytes / 1e6)
+                           if in_bytes > 126e6 else "inputs %.0f MB fit L2; not flushed" % (in_bytes / 1e6),
+                           p_operand="tmem" if args.flags & 1 else "smem"),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "kernel": "attn_fwd_kernel", "kernel_ms": ms_attn, "stage_kernel_ms": ms_stage,
+                         "flops_per_launch": flops, "peak_source": pk_src +
+                         (" burst" if total_s < 2.0 else " sustained")},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline(cfg, wl)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,7 @@ GTA_DTYPE_BF16, GTA_DTYPE_F32 = 0, 1
 GTA_FLAG_P_IN_TMEM = 1
 GTA_FLAG_SKIP_STAGE = 2
 GTA_FLAG_STAGE_ONLY = 4
+GTA_FLAG_V0_PIPELINE = 8
 
 
 class GtaReps(ctypes.Structure):
@@ -31,7 +32,7 @@ class GtaAttnParams(ctypes.Structure):
         + [(n, c_int) for n in ("B", "H", "Tq", "Tk", "D", "Nq", "Nk", "triv", "se3", "so3", "so2")]
         + [("reps", GtaReps), ("trans_coeff", c_void_p), ("scale", c_float)]
         + [(n, c_int) for n in ("in_dtype", "out_dtype", "v_transform")]
-        + [("workspace", c_void_p), ("workspace_bytes", c_size_t), ("flags", c_int)]
+        + [("workspace", c_void_p), ("workspace_bytes", c_size_t), ("flags", c_int), ("debug_clocks", c_void_p)]
     )
 
 

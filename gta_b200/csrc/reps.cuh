@@ -152,4 +152,80 @@ __device__ __forceinline__ void store_chunk<float>(float* p, const float* x) {
     reinterpret_cast<float4*>(p)[1] = make_float4(x[4], x[5], x[6], x[7]);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Latency-friendly variants: the per-view matrices are loaded ONCE per row into registers and the per-chunk
+// loads (raw data + SO(2) table) are issued for a whole group of chunks before any of them is consumed, so a row
+// costs ~2 global-load round trips instead of one per chunk.
+struct ViewReps {
+    float M[16];   // se3 4x4 of the row's view (unscaled)
+    float W[34];   // so3 D1 | D2 of the row's view
+};
+__device__ __forceinline__ void load_view_reps(ViewReps& vr, const HeadDims& hd, const float* __restrict__ se3m,
+                                               const float* __restrict__ so3m) {
+    if (hd.se3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 r = __ldg(reinterpret_cast<const float4*>(se3m) + i);
+            vr.M[4 * i] = r.x; vr.M[4 * i + 1] = r.y; vr.M[4 * i + 2] = r.z; vr.M[4 * i + 3] = r.w;
+        }
+    }
+    if (hd.so3) {
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            float2 r = __ldg(reinterpret_cast<const float2*>(so3m) + i);
+            vr.W[2 * i] = r.x; vr.W[2 * i + 1] = r.y;
+        }
+    }
+}
+// (cos,sin) x 4 pairs of chunk c of a token (valid only when chunk c lies in the so2 block).
+struct So2Chunk { float4 a, b; };
+__device__ __forceinline__ So2Chunk load_so2_chunk(const float* __restrict__ so2cs, int c, const HeadDims& hd) {
+    So2Chunk r;
+    r.a = make_float4(1.f, 0.f, 1.f, 0.f); r.b = r.a;
+    const int off = c * 8 - (hd.triv + hd.se3 + hd.so3);      // float index into the token's [C][2] table
+    if (hd.so2 && off >= 0) {
+        r.a = __ldg(reinterpret_cast<const float4*>(so2cs + off));
+        r.b = __ldg(reinterpret_cast<const float4*>(so2cs + off) + 1);
+    }
+    return r;
+}
+template <int kMode>
+__device__ __forceinline__ void apply_rep_chunk_pre(float* x, int c, const HeadDims& hd, const ViewReps& vr,
+                                                    const So2Chunk& sc, float tc) {
+    const int e = c * 8;
+    if (e < hd.triv) return;
+    if (e < hd.triv + hd.se3) {
+        if (kMode == kModeQ) se3_apply_T(x, vr.M, tc); else se3_apply(x, vr.M, tc);
+        return;
+    }
+    if (e < hd.triv + hd.se3 + hd.so3) {
+        if (kMode == kModeOut) so3_apply<true>(x, vr.W); else so3_apply<false>(x, vr.W);
+        return;
+    }
+    const float cs[8] = {sc.a.x, sc.a.y, sc.a.z, sc.a.w, sc.b.x, sc.b.y, sc.b.z, sc.b.w};
+    if (kMode == kModeOut) so2_apply<true>(x, cs); else so2_apply<false>(x, cs);
+}
+
+// Raw (unconverted) chunk loads so that several can be in flight before the first conversion.
+template <typename T> struct RawChunk;
+template <> struct RawChunk<__nv_bfloat16> { uint4 v; };
+template <> struct RawChunk<float> { float4 a, b; };
+__device__ __forceinline__ void load_raw(const __nv_bfloat16* __restrict__ p, RawChunk<__nv_bfloat16>& r) {
+    r.v = __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void load_raw(const float* __restrict__ p, RawChunk<float>& r) {
+    r.a = __ldg(reinterpret_cast<const float4*>(p));
+    r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void zero_raw(RawChunk<__nv_bfloat16>& r) { r.v = make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ void zero_raw(RawChunk<float>& r) { r.a = make_float4(0, 0, 0, 0); r.b = r.a; }
+__device__ __forceinline__ void raw_to_f32(const RawChunk<__nv_bfloat16>& r, float* x) {
+    x[0] = bf16_lo(r.v.x); x[1] = bf16_hi(r.v.x); x[2] = bf16_lo(r.v.y); x[3] = bf16_hi(r.v.y);
+    x[4] = bf16_lo(r.v.z); x[5] = bf16_hi(r.v.z); x[6] = bf16_lo(r.v.w); x[7] = bf16_hi(r.v.w);
+}
+__device__ __forceinline__ void raw_to_f32(const RawChunk<float>& r, float* x) {
+    x[0] = r.a.x; x[1] = r.a.y; x[2] = r.a.z; x[3] = r.a.w; x[4] = r.b.x; x[5] = r.b.y; x[6] = r.b.z; x[7] = r.b.w;
+}
+
 }  // namespace gta

@@ -114,7 +114,7 @@ def _params(q, k, v, out, reps: PackedReps, f_dims, trans_coeff, scale, v_transf
 def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: PackedReps, f_dims: dict, *,
                       trans_coeff: Optional[torch.Tensor] = None, scale: Optional[float] = None,
                       v_transform: bool = True, out_dtype: Optional[torch.dtype] = None,
-                      return_lse: bool = False, flags: int = 0):
+                      return_lse: bool = False, flags: int = 0, debug_clocks: Optional[torch.Tensor] = None):
     """q [B,H,Tq,D], k,v [B,H,Tk,D] (strided views allowed) -> out [B,H,Tq,D] as a permuted view of a
     contiguous [B,Tq,H,D] buffer (so the reference's 'b h n d -> b n (h d)' is free)."""
     B, H, Tq, D = q.shape
@@ -131,6 +131,7 @@ def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: P
     base = ws.data_ptr()
     p.workspace = (base + 1023) // 1024 * 1024
     p.workspace_bytes = nbytes
+    p.debug_clocks = _ptr(debug_clocks)
     check(lib().gta_attn_fwd(p, _stream()), "gta_attn_fwd")
     res = out.permute(0, 2, 1, 3)
     return (res, lse) if return_lse else res

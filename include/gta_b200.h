@@ -74,11 +74,13 @@ typedef struct GtaAttnParams {
     void* workspace;           /* >= gta_attn_fwd_workspace_bytes(...) bytes, 1024-byte aligned */
     size_t workspace_bytes;
     int flags;                 /* GTA_FLAG_* */
+    long long* debug_clocks;   /* optional [num_CTAs,8] clock64 phase stamps of the attention kernel (tools/phase_timing.py); NULL = off */
 } GtaAttnParams;
 
-#define GTA_FLAG_P_IN_TMEM 1   /* P operand of the PV MMA read from tensor memory instead of shared memory */
+#define GTA_FLAG_P_IN_TMEM 1   /* (v0 pipeline only) P operand of the PV MMA read from tensor memory */
 #define GTA_FLAG_SKIP_STAGE 2  /* workspace already holds K'/V' of these inputs: launch only the attention kernel */
 #define GTA_FLAG_STAGE_ONLY 4  /* launch only the K'/V' staging kernel (fills the workspace) */
+#define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 
 /* Scratch for the rotated K'/V' operand tiles. */
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D);

@@ -40,7 +40,7 @@ def test_struct_layout_matches_header_order():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(const\s+)?(void|float|int64_t|int|size_t|GtaReps)\s*\*?\s*", "", decl)
+        decl = re.sub(r"^(const\s+)?(void|float|int64_t|int|size_t|GtaReps|long long)\s*\*?\s*", "", decl)
         order += [d.strip().lstrip("*") for d in decl.split(",")]
     assert order == names
 

@@ -49,8 +49,10 @@ def _oracle(cfg, inp, tc=0.01):
                                   inp["extr_k"], inp["coord_q"], inp["coord_k"], trans_coeff=tc)
 
 
-def _tol(ref):
-    return BF16_TOL * max(1.0, float(np.abs(ref).max()))
+def _tol(ref, tc=0.01):
+    # trans_coeff = 1 feeds the (O(1)) camera translations into the se3 features: the rotated operands and the
+    # output grow with them and so does the bf16 rounding error -> budget relative to |ref|_max, doubled.
+    return BF16_TOL * max(1.0, float(np.abs(ref).max())) * (2.0 if tc >= 0.5 else 1.0)
 
 
 def test_umma_probe_exact():
@@ -115,7 +117,7 @@ def test_rotated_operands_match_oracle(dtype):
 
 @pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
                                         if "reps_" not in p))
-@pytest.mark.parametrize("flags", [0, 1])
+@pytest.mark.parametrize("flags", [0, 8, 9], ids=["v1", "v0_P_smem", "v0_P_tmem"])
 def test_golden_vectors(name, flags):
     """Committed outputs of the unmodified reference (fp32, CPU) vs the fused kernel fed the same fp32 inputs."""
     from tests.golden.gen_golden import CASES
@@ -127,7 +129,7 @@ def test_golden_vectors(name, flags):
     if not cross:
         inp["extr_q"], inp["coord_q"] = inp["extr_k"], inp["coord_k"]
     out = _run(cfg, inp, tc=float(g["trans_coeff"]), flags=flags)
-    assert np.abs(out - g["out"]).max() < _tol(g["out"])
+    assert np.abs(out - g["out"]).max() < _tol(g["out"], float(g["trans_coeff"]))
 
 
 CASES_GPU = [
@@ -147,7 +149,7 @@ CASES_GPU = [
 
 
 @pytest.mark.parametrize("case", CASES_GPU, ids=lambda c: f"D{c[0]['head_dim']}_{c[1]}x{c[3]}_{c[2]}x{c[4]}_{'x' if c[5] else 's'}_{str(c[7])[6:]}")
-@pytest.mark.parametrize("flags", [0, 1], ids=["P_smem", "P_tmem"])
+@pytest.mark.parametrize("flags", [0, 8, 9], ids=["v1", "v0_P_smem", "v0_P_tmem"])
 def test_fused_attention_matches_oracle(case, flags):
     base, nq, nk, tq, tk, cross, B, dtype, tc = case
     cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
@@ -155,7 +157,7 @@ def test_fused_attention_matches_oracle(case, flags):
     ref = _oracle(cfg, inp, tc)
     out = _run(cfg, inp, tc, flags)
     assert np.isfinite(out).all()
-    assert np.abs(out - ref).max() < _tol(ref)
+    assert np.abs(out - ref).max() < _tol(ref, tc)
 
 
 def test_contiguous_and_strided_inputs_agree():

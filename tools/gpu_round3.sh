@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python tools/phase_timing.py msn_enc 64 2>&1 | tee gpurun_out/phase_msn_enc.log
+timeout 300 python tools/phase_timing.py clevr_enc 32 2>&1 | tee gpurun_out/phase_clevr_enc.log
+for wl in msn_enc msn_dec clevr_enc clevr_dec; do
+  timeout 300 python bench.py --workload $wl --no-cpu --no-e2e --steps 50 > gpurun_out/bench3_$wl.json 2>gpurun_out/bench3_$wl.err; python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/bench3_$wl.json")); r=d["roofline"]; print("$wl", round(d["value"],1), "Mtok/s step_ms", round(d["ms_per_step"],3), "attn_ms", round(r["kernel_ms"],3), "stage_ms", round(r["stage_kernel_ms"],3), "frac", round(r["frac"],3), d["clocks"])
+except Exception as e: print("$wl failed", e); print(open("gpurun_out/bench3_$wl.err").read()[-1500:])
+PY
+done
