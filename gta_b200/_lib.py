@@ -10,13 +10,15 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgta_b200.so")
+# GTA_B200_LIB selects a tuning build of the same library (python -m gta_b200.build -D... --out ...)
+LIB_PATH = os.environ.get("GTA_B200_LIB") or os.path.join(_HERE, "libgta_b200.so")
 
 GTA_DTYPE_BF16, GTA_DTYPE_F32 = 0, 1
 GTA_FLAG_P_IN_TMEM = 1
 GTA_FLAG_SKIP_STAGE = 2
 GTA_FLAG_STAGE_ONLY = 4
 GTA_FLAG_V0_PIPELINE = 8
+GTA_FLAG_V1_PIPELINE = 16
 
 
 class GtaReps(ctypes.Structure):

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgta_b200.so")
-SOURCES = ["gta_abi.cu", "gta_reps.cu", "gta_rotate_kv.cu", "gta_attn_fwd.cu", "gta_attn_fwd2.cu"]
+SOURCES = ["gta_abi.cu", "gta_reps.cu", "gta_rotate_kv.cu", "gta_attn_fwd.cu", "gta_attn_fwd2.cu", "gta_attn_fwd3.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -31,14 +31,15 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    if not force and not defines and out == OUT and not _stale():
         return OUT
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + ("_" + "_".join(d.replace("=", "") for d in defines) if defines else ""))
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     common = [nvcc, *ARCH, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-I", os.path.join(HERE, "..", "include")]
+    common += ["-D" + d for d in defines]
     if verbose:
         common += ["-Xptxas", "-v"]
     objs = []
@@ -49,14 +50,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         procs.append((src, subprocess.Popen(common + ["-c", os.path.join(CSRC, src), "-o", obj],
                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode:
-            sys.stderr.write(out)
+            sys.stderr.write(log)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", OUT, *objs, "-lcudart"])
-    return OUT
+    subprocess.check_call([nvcc, *ARCH, "-shared", "-o", out, *objs, "-lcudart"])
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    # tuning variants: python -m gta_b200.build -DGTA_POLY_NUM=1 --out gta_b200/libgta_b200_p14.so
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else OUT
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=os.path.abspath(out)))

@@ -26,6 +26,7 @@ int launch_rotate_kv(const GtaAttnParams& p, cudaStream_t st);
 int launch_rotate_debug(const GtaAttnParams& p, float* qt, float* kt, float* vt, cudaStream_t st);
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);
+int launch_attn_fwd_v2(const GtaAttnParams& p, cudaStream_t st);
 int launch_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem, float* outS,
                       float* outO, cudaStream_t st);
 

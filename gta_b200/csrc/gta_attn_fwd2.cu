@@ -187,14 +187,14 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd2_kernel(const AttnArgs 
                 l_run *= alpha;
                 m_used = m_new;
                 if (j > 0) {
-#pragma unroll
-                    for (int cb = 0; cb < D / 32; ++cb) {
-                        uint32_t o[32];
-                        tmem_ld32(o_addr + cb * 32, o);
+#pragma unroll 1
+                    for (int c8 = 0; c8 < D / 8; ++c8) {      // rare: keep the footprint at 8 registers
+                        uint32_t o8[8];
+                        tmem_ld8(o_addr + c8 * 8, o8);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                        tmem_st32(o_addr + cb * 32, o);
+                        for (int i = 0; i < 8; ++i) o8[i] = __float_as_uint(__uint_as_float(o8[i]) * alpha);
+                        tmem_st8(o_addr + c8 * 8, o8);
                     }
                 }
             }
@@ -205,16 +205,17 @@ __global__ void __launch_bounds__(kThreads2, 1) attn_fwd2_kernel(const AttnArgs 
             uint64_t lsum2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                uint32_t pr[32];
+                // packed in place: P pair i overwrites sreg[half*64 + i] after s[half*64 + 2i], s[.. + 2i+1] were consumed,
+                // so the store reuses the register block the load filled (no second 32-register block is needed)
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     float x0, x1;
                     unpack_f32x2(ffma2(pack_f32x2(s[half * 64 + 2 * i], s[half * 64 + 2 * i + 1]), cs2, neg2), x0, x1);
                     const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
                     lsum2 = fadd2(lsum2, pack_f32x2(p0, p1));
-                    pr[i] = pack_bf16x2(p0, p1);
+                    sreg[half * 64 + i] = pack_bf16x2(p0, p1);
                 }
-                tmem_st32(s_addr + half * 32, pr);
+                tmem_st32(s_addr + half * 32, sreg + half * 64);
             }
             float ls0, ls1;
             unpack_f32x2(lsum2, ls0, ls1);
@@ -372,6 +373,7 @@ static int launch2_d(const AttnArgs& a, int D, dim3 grid, cudaStream_t st) {
 
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st) {
     if (p.flags & GTA_FLAG_V0_PIPELINE) return launch_attn_fwd_v0(p, st);
+    if (!(p.flags & GTA_FLAG_V1_PIPELINE) && p.D <= 96) return launch_attn_fwd_v2(p, st);   // persistent pipeline
     const AttnArgs a = make_attn_args(p);
     dim3 grid((p.Tq + 255) / 256, p.H, p.B);
     const bool ib = p.in_dtype == GTA_DTYPE_BF16, ob = p.out_dtype == GTA_DTYPE_BF16;

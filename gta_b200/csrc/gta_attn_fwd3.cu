@@ -1,0 +1,451 @@
+// Fused GTA attention forward, v2 pipeline: PERSISTENT CTAs (one per SM), two 128-query tiles per work item,
+// Q staging of the NEXT item and the epilogue of the PREVIOUS item overlapped with the tensor-core main loop.
+//
+// Work item = (batch b, head h, query pair p): 256 query rows of one (b,h) against all Tk keys.
+// CTA c processes items c, c+grid, c+2*grid, ... (all items cost the same, so static striding is balanced).
+//
+//   warps 0-3   softmax warpgroup A   thread i <-> query row i of tile A <-> TMEM lane i
+//   warps 4-7   softmax warpgroup B
+//   warp  8     UMMA issuer (one lane)
+//   warp  9     bulk-copy producer for the K'/V' tile images (2-stage ring, runs ahead across item boundaries)
+//   warps 10-11 Q stager: loads the raw strided Q rows of the NEXT item, applies rho_q^{-T} in fp32 registers and
+//               writes the bf16 UMMA operand tiles into the other half of a double-buffered Q area
+// Register split (setmaxnreg): softmax warpgroups 200, the third warpgroup 96 (384 threads, 65 536 registers).
+//
+// Per key tile the tensor pipe executes  PV_A(j) QK_A(j+1) PV_B(j) QK_B(j+1)  (see gta_attn_fwd2.cu); at an item
+// boundary QK_X(0) of the next item is issued right after PV_X(n-1), so S of the next item is ready while the
+// softmax warpgroup is still writing out the previous item's O.  O_X in TMEM is recycled through o_final/o_free.
+//
+// Reference semantics: source/utils/gta.py:92-279 and source/layers.py:202-211.
+#include <cmath>
+
+#include "attn_common.cuh"
+
+namespace gta {
+
+constexpr int kThreads3 = 384;
+constexpr int kStagerThreads = 64;
+constexpr uint32_t k3TmemSA = 0, k3TmemSB = 128, k3TmemOA = 256, k3TmemOB = 384;
+constexpr float k3RescaleThreshold = 8.0f;   // log2 units
+// Fraction of the exponentials evaluated with poly_exp2x2 instead of MUFU.EX2: pairs with (i % DEN) < NUM.
+#ifndef GTA_POLY_NUM
+#define GTA_POLY_NUM 0
+#endif
+#ifndef GTA_POLY_DEN
+#define GTA_POLY_DEN 4
+#endif
+
+template <int D>
+struct Attn3Cfg {
+    static constexpr int kStages = 2;
+    static constexpr uint32_t kTile = 128u * D * 2u;
+    static constexpr uint32_t kQ = 0;                          // [2 buffers][2 tiles]
+    static constexpr uint32_t kK = 4 * kTile;                  // [kStages]
+    static constexpr uint32_t kV = kTile * (4 + kStages);      // [kStages]
+    static constexpr uint32_t kBars = kTile * (4 + 2 * kStages);
+    enum : int {
+        bQFull = 0,                        // [buf][X]  count 128 (stager threads)
+        bQFree = 4,                        // [buf][X]  tcgen05.commit after the item's last QK_X
+        bKFull = 8,                        // [kStages]
+        bVFull = bKFull + kStages,
+        bKEmpty = bVFull + kStages,
+        bVEmpty = bKEmpty + kStages,
+        bSFull = bVEmpty + kStages,        // [X] commit
+        bPFull = bSFull + 2,               // [X] count 128
+        bOFinal = bPFull + 2,              // [X] commit after the item's last PV_X
+        bOFree = bOFinal + 2,              // [X] count 128: O_X drained to registers
+        bCount = bOFree + 2
+    };
+    static constexpr uint32_t kTmemSlot = kBars + bCount * 8;
+    static constexpr uint32_t kUsed = kTmemSlot + 16;
+    static constexpr uint32_t kBytes = (kUsed + 1024 > 120u * 1024u) ? kUsed + 1024 : 120u * 1024u;
+};
+
+struct ItemCoord {
+    int b, h, p;
+    bool has_b;
+};
+__device__ __forceinline__ ItemCoord decode_item(int item, int npairs, int H, int Tq) {
+    ItemCoord c;
+    c.p = item % npairs;
+    const int bh = item / npairs;
+    c.h = bh % H;
+    c.b = bh / H;
+    c.has_b = (c.p * 256 + 128) < Tq;
+    return c;
+}
+
+template <typename TIn, typename TOut, int D>
+__global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs a, const int npairs, const int nitems) {
+    using L = Attn3Cfg<D>;
+    constexpr int NS = L::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = a.ntiles_k;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&bars[L::bQFull + i], kStagerThreads);
+            mbar_init(&bars[L::bQFree + i], 1);
+        }
+        for (int x = 0; x < 2; ++x) {
+            mbar_init(&bars[L::bSFull + x], 1);
+            mbar_init(&bars[L::bPFull + x], 128);
+            mbar_init(&bars[L::bOFinal + x], 1);
+            mbar_init(&bars[L::bOFree + x], 128);
+        }
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&bars[L::bKFull + s], 1);
+            mbar_init(&bars[L::bVFull + s], 1);
+            mbar_init(&bars[L::bKEmpty + s], 1);
+            mbar_init(&bars[L::bVEmpty + s], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 8) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const float tc = a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f;
+
+    if (warp < 8) {
+        // =========================================================== softmax warpgroups (+ epilogue)
+        setmaxnreg_inc<200>();
+        const int X = warp >> 2;
+        const int r = threadIdx.x & 127;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const uint32_t s_addr = lane_base + (X ? k3TmemSB : k3TmemSA);
+        const uint32_t o_addr = lane_base + (X ? k3TmemOB : k3TmemOA);
+        const float cs = a.scale_log2;
+        const uint64_t cs2 = pack_f32x2(cs, cs);
+        uint32_t gt = 0;      // tiles processed by this warpgroup (s_full / p_full phase)
+        uint32_t cnt = 0;     // items processed by this warpgroup (o_final phase)
+
+#pragma unroll 1
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const ItemCoord ic = decode_item(item, npairs, a.H, a.Tq);
+            if (X == 1 && !ic.has_b) continue;
+            float m_used = -INFINITY, l_run = 0.f;
+
+#pragma unroll 1
+            for (int j = 0; j < n; ++j, ++gt) {
+                mbar_wait(&bars[L::bSFull + X], gt & 1);
+                tc_fence_after();
+                uint32_t sreg[128];
+                tmem_ld32(s_addr, sreg);
+                tmem_ld32(s_addr + 32, sreg + 32);
+                tmem_ld32(s_addr + 64, sreg + 64);
+                tmem_ld32(s_addr + 96, sreg + 96);
+                tmem_ld_wait();
+                float* s = reinterpret_cast<float*>(sreg);
+                if (j == n - 1) {
+                    const int nvalid = a.Tk - j * 128;
+                    if (nvalid < 128) {
+#pragma unroll
+                        for (int i = 0; i < 128; ++i) if (i >= nvalid) s[i] = -INFINITY;
+                    }
+                }
+                float mx0 = fmax3(s[0], s[1], s[2]), mx1 = fmax3(s[3], s[4], s[5]);
+                float mx2 = fmax3(s[6], s[7], s[8]), mx3 = fmax3(s[9], s[10], s[11]);
+#pragma unroll
+                for (int i = 12; i < 124; i += 8) {
+                    mx0 = fmax3(mx0, s[i], s[i + 1]); mx1 = fmax3(mx1, s[i + 2], s[i + 3]);
+                    mx2 = fmax3(mx2, s[i + 4], s[i + 5]); mx3 = fmax3(mx3, s[i + 6], s[i + 7]);
+                }
+                mx0 = fmax3(mx0, s[124], s[125]); mx1 = fmax3(mx1, s[126], s[127]);
+                const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+
+                const bool grow = (m_tile - m_used) * cs > k3RescaleThreshold;   // always true on the item's first tile
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float m_new = grow ? m_tile : m_used;
+                    const float alpha = grow ? fast_exp2((m_used - m_new) * cs) : 1.0f;
+                    l_run *= alpha;
+                    m_used = m_new;
+                    if (j > 0) {
+#pragma unroll 1
+                        for (int c8 = 0; c8 < D / 8; ++c8) {      // rare: keep the footprint at 8 registers
+                            uint32_t o8[8];
+                            tmem_ld8(o_addr + c8 * 8, o8);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o8[i] = __float_as_uint(__uint_as_float(o8[i]) * alpha);
+                            tmem_st8(o_addr + c8 * 8, o8);
+                        }
+                    }
+                }
+
+                const float neg = -m_used * cs;
+                const uint64_t neg2 = pack_f32x2(neg, neg);
+                uint64_t lsum2 = pack_f32x2(0.f, 0.f);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    // packed in place: P pair i overwrites sreg[half*64 + i] after s[half*64 + 2i], s[.. + 2i+1] were consumed,
+                    // so the store reuses the register block the load filled (no second 32-register block is needed)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint64_t x2 = ffma2(pack_f32x2(s[half * 64 + 2 * i], s[half * 64 + 2 * i + 1]), cs2, neg2);
+                        float p0, p1;
+                        if ((i % GTA_POLY_DEN) < GTA_POLY_NUM) {
+                            poly_exp2x2(x2, p0, p1);
+                        } else {
+                            float x0, x1;
+                            unpack_f32x2(x2, x0, x1);
+                            p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+                        }
+                        lsum2 = fadd2(lsum2, pack_f32x2(p0, p1));
+                        sreg[half * 64 + i] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st32(s_addr + half * 32, sreg + half * 64);
+                }
+                float ls0, ls1;
+                unpack_f32x2(lsum2, ls0, ls1);
+                l_run += ls0 + ls1;
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[L::bPFull + X]);
+            }
+
+            // ---- epilogue of this item: prefetch the row's reps, drain O to registers, release O, then finish.
+            const int t = ic.p * 256 + X * 128 + r;
+            const bool valid = t < a.Tq;
+            const int tt = valid ? t : a.Tq - 1;
+            ViewReps vr;
+            const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
+            if (a.v_transform) {
+                const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
+                load_view_reps(vr, a.hd, a.se3_q + view * 16, a.so3_q + view * 34);
+            }
+            mbar_wait(&bars[L::bOFinal + X], cnt & 1);
+            ++cnt;
+            tc_fence_after();
+            uint32_t o[D];
+#pragma unroll
+            for (int cb = 0; cb < D / 32; ++cb) tmem_ld32(o_addr + cb * 32, o + cb * 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[L::bOFree + X]);          // the next item's PV_X(0) may overwrite O_X now
+
+            const float inv_l = 1.0f / l_run;
+            TOut* orow = reinterpret_cast<TOut*>(a.out) + ((static_cast<int64_t>(ic.b) * a.Tq + tt) * a.H + ic.h) * D;
+#pragma unroll
+            for (int cp = 0; cp < D / 16; ++cp) {
+                So2Chunk sc[2];
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) sc[cc] = load_so2_chunk(so2, cp * 2 + cc, a.hd);
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = cp * 2 + cc;
+                    float x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(o[c * 8 + i]) * inv_l;
+                    if (a.v_transform) apply_rep_chunk_pre<kModeOut>(x, c, a.hd, vr, sc[cc], tc);
+                    if (valid) store_chunk<TOut>(orow + c * 8, x);
+                }
+            }
+            if (a.lse && valid)
+                a.lse[(static_cast<int64_t>(ic.b) * a.H + ic.h) * a.Tq + t] = m_used * a.scale + logf(l_run);
+        }
+    } else {
+      setmaxnreg_dec<96>();
+      if (warp >= 10) {
+        // =========================================================== Q stager (runs one item ahead)
+        const int r0 = threadIdx.x - 320;    // 0..63; this thread stages rows r0 and r0 + 64 of each tile
+        uint32_t cntx[2] = {0, 0};          // items staged per tile slot (buffer = cnt & 1, phase = (cnt >> 1) & 1)
+#pragma unroll 1
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const ItemCoord ic = decode_item(item, npairs, a.H, a.Tq);
+#pragma unroll 1
+            for (int X = 0; X < 2; ++X) {
+                if (X == 1 && !ic.has_b) continue;
+                const uint32_t c_ = cntx[X]++;
+                const int buf = c_ & 1;
+                if (c_ >= 2) mbar_wait(&bars[L::bQFree + buf * 2 + X], ((c_ >> 1) - 1) & 1);
+                uint8_t* sQ = smem + L::kQ + (buf * 2 + X) * L::kTile;
+#pragma unroll 1
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int r = r0 + rr * 64;
+                    const int t = ic.p * 256 + X * 128 + r;
+                    const bool valid = t < a.Tq;
+                    const int tt = valid ? t : a.Tq - 1;
+                    const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
+                    const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
+                    const TIn* qrow = reinterpret_cast<const TIn*>(a.q) + static_cast<int64_t>(ic.b) * a.q_sb +
+                                      static_cast<int64_t>(ic.h) * a.q_sh + static_cast<int64_t>(tt) * a.q_st;
+                    constexpr int NC = D / 8;
+                    constexpr int G = (sizeof(TIn) == 2) ? NC : ((NC % 6 == 0) ? 6 : 4);   // <= 48 registers of raw data
+                    const float* se3 = a.se3_q + view * 16;
+                    const float* so3 = a.so3_q + view * 34;
+#pragma unroll 1
+                    for (int g = 0; g < NC / G; ++g) {
+                        RawChunk<TIn> raw[G];
+#pragma unroll
+                        for (int i = 0; i < G; ++i) {
+                            zero_raw(raw[i]);
+                            if (valid) load_raw(qrow + (g * G + i) * 8, raw[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < G; ++i) {
+                            float x[8];
+                            raw_to_f32(raw[i], x);
+                            apply_rep_chunk<kModeQ>(x, g * G + i, a.hd, se3, so3, so2, tc);
+                            *reinterpret_cast<uint4*>(sQ + tile_sw64_offset(r, g * G + i)) = pack_chunk_bf16(x);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bars[L::bQFull + buf * 2 + X]);
+            }
+        }
+      } else if (warp == 8) {
+            // ======================================================= UMMA issuer
+            constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
+            uint32_t gk = 0;                   // global key-tile counter of this CTA (K/V ring position)
+            uint32_t gtx[2] = {0, 0};          // tiles per softmax warpgroup (p_full phase)
+            uint32_t cntx[2] = {0, 0};         // items per tile slot (Q buffer / o_free phase)
+
+#pragma unroll 1
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const ItemCoord ic = decode_item(item, npairs, a.H, a.Tq);
+                const int nx = ic.has_b ? 2 : 1;
+                uint32_t q_addr[2];
+                for (int X = 0; X < nx; ++X) {
+                    const uint32_t c_ = cntx[X];
+                    const int buf = c_ & 1;
+                    q_addr[X] = smem_u32(smem + L::kQ + (buf * 2 + X) * L::kTile);
+                }
+
+                auto issue_qk = [&](int X, int j) {
+                    const int s = (gk + j) % NS;
+                    if (lane == 0) {
+                        const uint32_t k_addr = smem_u32(smem + L::kK + s * L::kTile);
+                        const uint32_t d_addr = tmem_base + (X ? k3TmemSB : k3TmemSA);
+#pragma unroll
+                        for (int kk = 0; kk < D / 16; ++kk)
+                            umma_ss(d_addr, desc_kmajor_sw64(q_addr[X], kk), desc_kmajor_sw64(k_addr, kk), idesc_qk, kk > 0);
+                        if (X == nx - 1) umma_commit(&bars[L::bKEmpty + s]);
+                        if (j == n - 1) umma_commit(&bars[L::bQFree + (cntx[X] & 1) * 2 + X]);
+                        umma_commit(&bars[L::bSFull + X]);
+                    }
+                    __syncwarp();
+                };
+                auto issue_pv = [&](int X, int j) {
+                    const int s = (gk + j) % NS;
+                    mbar_wait(&bars[L::bPFull + X], (gtx[X] + j) & 1);
+                    if (j == 0 && cntx[X] > 0) mbar_wait(&bars[L::bOFree + X], (cntx[X] - 1) & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t v_addr = smem_u32(smem + L::kV + s * L::kTile);
+                        const uint32_t d_addr = tmem_base + (X ? k3TmemOB : k3TmemOA);
+                        const uint32_t p_addr = tmem_base + (X ? k3TmemSB : k3TmemSA);
+#pragma unroll
+                        for (int kk = 0; kk < 8; ++kk)
+                            umma_ts(d_addr, p_addr + kk * 8, desc_mnmajor_sw64(v_addr, kk), idesc_pv,
+                                    (j > 0 || kk > 0) ? 1u : 0u);
+                        if (X == nx - 1) umma_commit(&bars[L::bVEmpty + s]);
+                        if (j == n - 1) umma_commit(&bars[L::bOFinal + X]);
+                    }
+                    __syncwarp();
+                };
+
+                mbar_wait(&bars[L::bKFull + gk % NS], (gk / NS) & 1);
+                for (int X = 0; X < nx; ++X) {
+                    const uint32_t c_ = cntx[X];
+                    mbar_wait(&bars[L::bQFull + (c_ & 1) * 2 + X], (c_ >> 1) & 1);
+                    tc_fence_after();
+                    issue_qk(X, 0);
+                }
+#pragma unroll 1
+                for (int j = 0; j < n; ++j) {
+                    mbar_wait(&bars[L::bVFull + (gk + j) % NS], ((gk + j) / NS) & 1);
+                    if (j + 1 < n) mbar_wait(&bars[L::bKFull + (gk + j + 1) % NS], ((gk + j + 1) / NS) & 1);
+                    for (int X = 0; X < nx; ++X) {
+                        issue_pv(X, j);
+                        if (j + 1 < n) issue_qk(X, j + 1);
+                    }
+                }
+                gk += n;
+                for (int X = 0; X < nx; ++X) { gtx[X] += n; ++cntx[X]; }
+            }
+      } else if (warp == 9) {
+            // ======================================================= bulk-copy producer
+            uint32_t gk = 0;
+#pragma unroll 1
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const ItemCoord ic = decode_item(item, npairs, a.H, a.Tq);
+                const size_t blob0 = (static_cast<size_t>(ic.b) * a.H + ic.h) * n;
+#pragma unroll 1
+                for (int j = 0; j < n; ++j, ++gk) {
+                    const int s = gk % NS;
+                    if (gk >= NS) mbar_wait(&bars[L::bKEmpty + s], ((gk / NS) - 1) & 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&bars[L::bKFull + s], L::kTile);
+                        bulk_g2s(smem + L::kK + s * L::kTile, a.ws_k + (blob0 + j) * L::kTile, L::kTile, &bars[L::bKFull + s]);
+                    }
+                    if (gk >= NS) mbar_wait(&bars[L::bVEmpty + s], ((gk / NS) - 1) & 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&bars[L::bVFull + s], L::kTile);
+                        bulk_g2s(smem + L::kV + s * L::kTile, a.ws_v + (blob0 + j) * L::kTile, L::kTile, &bars[L::bVFull + s]);
+                    }
+                    __syncwarp();
+                }
+            }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+template <typename TIn, typename TOut, int D>
+static int launch3_one(const AttnArgs& a, const GtaAttnParams& p, cudaStream_t st) {
+    using L = Attn3Cfg<D>;
+    auto kern = attn_fwd3_kernel<TIn, TOut, D>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::kBytes));
+    if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int npairs = (p.Tq + 255) / 256;
+    const long long nitems = static_cast<long long>(p.B) * p.H * npairs;
+    if (nitems > 0x7fffffffLL) return set_error(GTA_ERR_UNSUPPORTED, "too many work items");
+    const int grid = static_cast<int>(nitems < num_sms ? nitems : num_sms);
+    kern<<<grid, kThreads3, L::kBytes, st>>>(a, npairs, static_cast<int>(nitems));
+    return check_launch("gta_attn_fwd");
+}
+
+template <typename TIn, typename TOut>
+static int launch3_d(const AttnArgs& a, const GtaAttnParams& p, cudaStream_t st) {
+    switch (p.D) {
+        case 32: return launch3_one<TIn, TOut, 32>(a, p, st);
+        case 64: return launch3_one<TIn, TOut, 64>(a, p, st);
+        case 96: return launch3_one<TIn, TOut, 96>(a, p, st);
+    }
+    return set_error(GTA_ERR_UNSUPPORTED, "persistent pipeline supports head dims 32/64/96");
+}
+
+int launch_attn_fwd_v2(const GtaAttnParams& p, cudaStream_t st) {
+    const AttnArgs a = make_attn_args(p);
+    const bool ib = p.in_dtype == GTA_DTYPE_BF16, ob = p.out_dtype == GTA_DTYPE_BF16;
+    if (ib && ob) return launch3_d<__nv_bfloat16, __nv_bfloat16>(a, p, st);
+    if (ib && !ob) return launch3_d<__nv_bfloat16, float>(a, p, st);
+    if (!ib && ob) return launch3_d<float, __nv_bfloat16>(a, p, st);
+    return launch3_d<float, float>(a, p, st);
+}
+
+}  // namespace gta

@@ -167,6 +167,18 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+// .x8 variants (8 consecutive columns) for the rarely taken accumulator-rescale path: small register footprint.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------ misc math
@@ -207,6 +219,29 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
+// 2^x for a pair of fp32 values on the FMA/ALU pipes instead of the 4-lane/clk MUFU unit (the softmax of a
+// 128x128 tile needs 16 K exponentials = 1024 clk of MUFU per SM sub-partition, more than the tile's tensor time at
+// head dim 96).  Round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f (max relative
+// error 7.5e-5, far below the bf16 rounding of P), exponent inserted with an integer shift-add.  x is clamped at -126.
+__device__ __forceinline__ void poly_exp2x2(uint64_t x2, float& r0, float& r1) {
+    float x0, x1;
+    unpack_f32x2(x2, x0, x1);
+    x2 = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const uint64_t magic2 = pack_f32x2(12582912.0f, 12582912.0f);
+    const uint64_t nmagic2 = pack_f32x2(-12582912.0f, -12582912.0f);
+    const uint64_t mone2 = pack_f32x2(-1.0f, -1.0f);
+    const uint64_t t2 = fadd2(x2, magic2);                 // low mantissa bits = round(x)
+    const uint64_t f2 = ffma2(fadd2(t2, nmagic2), mone2, x2);   // x - round(x)
+    uint64_t p2 = ffma2(pack_f32x2(0.0551716685f, 0.0551716685f), f2, pack_f32x2(0.242611125f, 0.242611125f));
+    p2 = ffma2(p2, f2, pack_f32x2(0.693260968f, 0.693260968f));
+    p2 = ffma2(p2, f2, pack_f32x2(0.999928057f, 0.999928057f));
+    float p0, p1, t0, t1;
+    unpack_f32x2(p2, p0, p1);
+    unpack_f32x2(t2, t0, t1);
+    r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));

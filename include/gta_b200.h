@@ -81,6 +81,7 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_SKIP_STAGE 2  /* workspace already holds K'/V' of these inputs: launch only the attention kernel */
 #define GTA_FLAG_STAGE_ONLY 4  /* launch only the K'/V' staging kernel (fills the workspace) */
 #define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
+#define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
 
 /* Scratch for the rotated K'/V' operand tiles. */
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D);

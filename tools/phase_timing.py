@@ -30,7 +30,7 @@ def main():
     for _ in range(3):
         ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc)
     dbg = torch.zeros(nct, 8, dtype=torch.int64, device=dev)
-    ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, debug_clocks=dbg)
+    ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, debug_clocks=dbg, flags=_lib.GTA_FLAG_V1_PIPELINE)
     torch.cuda.synchronize()
     d = dbg.cpu().double()
     t0 = d[:, 0].min()
