@@ -31,6 +31,12 @@ WORKLOADS = {
     "clevr_enc": (CLEVR, 2, 2, 300, 300, False, 32, "runs/clevrtr/GTA/gta encoder self-attention, 2 views x 15x20 tokens"),
     "clevr_dec": (CLEVR, 3, 2, 853, 300, True, 32, "runs/clevrtr/GTA/gta decoder cross-attention, Tq=2559, Tk=600"),
     "cfg1": (CFG1_A, 2, 2, 1024, 1024, False, 2, "BASELINE config 1: 2 views x 32x32, d=128, 4 heads"),
+    # BASELINE config 4: sequence-length sweep, B=1, d=768 (8 heads x 96), N views x 128x128 tokens (L = N*16384).
+    # The reference cannot run these (its [B,H,L,L] score matrix would be >= 34 GB); inputs are generated on the device.
+    "sweep2": (MSN_SO3, 2, 2, 16384, 16384, False, 1, "seq-len sweep: 2 views x 128x128 tokens, L=32768, d=768"),
+    "sweep5": (MSN_SO3, 5, 5, 16384, 16384, False, 1, "seq-len sweep: 5 views x 128x128 tokens, L=81920, d=768"),
+    "sweep10": (MSN_SO3, 10, 10, 16384, 16384, False, 1, "seq-len sweep: 10 views x 128x128 tokens, L=163840, d=768"),
+    "sweep20": (MSN_SO3, 20, 20, 16384, 16384, False, 1, "seq-len sweep: 20 views x 128x128 tokens, L=327680, d=768"),
 }
 METRIC = "GTA-attention Mtokens/sec"
 UNIT = "Mtokens/s"

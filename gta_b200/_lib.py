@@ -19,6 +19,7 @@ GTA_FLAG_SKIP_STAGE = 2
 GTA_FLAG_STAGE_ONLY = 4
 GTA_FLAG_V0_PIPELINE = 8
 GTA_FLAG_V1_PIPELINE = 16
+GTA_FLAG_V3_PIPELINE = 32
 
 
 class GtaReps(ctypes.Structure):
@@ -47,6 +48,7 @@ SYMBOLS = {
     "gta_so2_mats": (c_int, [c_void_p, c_int64, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),
     "gta_wigner_d": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gta_umma_probe": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 3),
+    "gta_umma_bench": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gta_last_error": (c_char_p, []),
     "gta_abi_version": (c_int, []),
 }

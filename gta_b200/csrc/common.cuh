@@ -27,6 +27,8 @@ int launch_rotate_debug(const GtaAttnParams& p, float* qt, float* kt, float* vt,
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v2(const GtaAttnParams& p, cudaStream_t st);
+int launch_attn_fwd_v3(const GtaAttnParams& p, cudaStream_t st);
+int launch_umma_bench(int D, int mode, int reps, int grid, long long* out, cudaStream_t st);
 int launch_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem, float* outS,
                       float* outO, cudaStream_t st);
 

@@ -111,4 +111,8 @@ int gta_umma_probe(const void* A, const void* Bm, const void* P, const void* V, 
     return launch_umma_probe(A, Bm, P, V, D, p_in_tmem, outS, outO, static_cast<cudaStream_t>(stream));
 }
 
+int gta_umma_bench(int D, int mode, int reps, int grid, long long* out, void* stream) {
+    return launch_umma_bench(D, mode, reps, grid, out, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

@@ -442,4 +442,87 @@ int launch_umma_probe(const void* A, const void* Bm, const void* P, const void* 
     return set_error(GTA_ERR_UNSUPPORTED, "gta_umma_probe: head dim %d not in {32,64,96,128}", D);
 }
 
+
+// ===================================================================================================
+// UMMA throughput micro-benchmark (tools/umma_bench.py): one CTA per SM, one thread issues `reps` repetitions of an
+// MMA group on garbage operands and measures clock64 from first issue to the completion commit.
+//   mode 0: S = Q K^T group, SS, M=128 N=128, K-steps D/16 (both operands K-major, 64B swizzle)
+//   mode 1: same with N=64
+//   mode 2: O += P V group, TS (A in TMEM), M=128 N=D, 8 K-steps (B MN-major, 64B swizzle)
+//   mode 3: O += P V group, SS (A = P tile in smem, 128B swizzle), 8 K-steps
+//   mode 4: mode 2 with 4 K-steps (64-key half tile)
+template <int D>
+__global__ void __launch_bounds__(128, 1) umma_bench_kernel(int mode, int reps, long long* out) {
+    constexpr uint32_t kTile = 128u * D * 2u;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 3 * kTile + 32768);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 2);
+    const int warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < (3 * kTile + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); fence_mbar_init(); }
+    if (warp == 0) { tmem_alloc(slot, 512); tmem_relinquish(); }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *reinterpret_cast<volatile uint32_t*>(slot);
+    if (threadIdx.x == 0) {
+        const uint32_t a_addr = smem_u32(smem), b_addr = smem_u32(smem + kTile), v_addr = smem_u32(smem + 2 * kTile);
+        const uint32_t p_addr = smem_u32(smem + 3 * kTile);
+        constexpr uint32_t id128 = make_idesc_bf16(128, 128, 0, 0), id64 = make_idesc_bf16(128, 64, 0, 0);
+        constexpr uint32_t idpv = make_idesc_bf16(128, D, 0, 1);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+            if (mode == 0) {
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ss(tb + (r & 1) * 128, desc_kmajor_sw64(a_addr, kk), desc_kmajor_sw64(b_addr, kk), id128, kk > 0);
+            } else if (mode == 1) {
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ss(tb + (r & 3) * 64, desc_kmajor_sw64(a_addr, kk), desc_kmajor_sw64(b_addr + (r & 1) * 4096, kk), id64, kk > 0);
+            } else if (mode == 2) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_ts(tb + 256 + (r & 1) * 128, tb + kk * 8, desc_mnmajor_sw64(v_addr, kk), idpv, 1u);
+            } else if (mode == 3) {
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_ss(tb + 256 + (r & 1) * 128, desc_p_sw128(p_addr, kk), desc_mnmajor_sw64(v_addr, kk), idpv, 1u);
+            } else {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_ts(tb + 256 + (r & 1) * 128, tb + kk * 8, desc_mnmajor_sw64(v_addr, (r & 1) * 4 + kk), idpv, 1u);
+            }
+        }
+        const long long t1 = clock64();
+        umma_commit(&bar[0]);
+        mbar_wait(&bar[0], 0);
+        const long long t2 = clock64();
+        out[blockIdx.x * 2] = t1 - t0;      // issue time
+        out[blockIdx.x * 2 + 1] = t2 - t0;  // until everything completed
+    }
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tb, 512); }
+}
+
+int launch_umma_bench(int D, int mode, int reps, int grid, long long* out, cudaStream_t st) {
+    const int bytes = 3 * 128 * D * 2 + 32768 + 64 + 1024;
+#define GTA_UB_CASE(DD)                                                                                          \
+    case DD: {                                                                                                   \
+        auto kern = umma_bench_kernel<DD>;                                                                       \
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);                          \
+        kern<<<grid, 128, bytes, st>>>(mode, reps, out);                                                         \
+        return check_launch("gta_umma_bench");                                                                   \
+    }
+    switch (D) {
+        GTA_UB_CASE(64)
+        GTA_UB_CASE(96)
+        GTA_UB_CASE(128)
+    }
+#undef GTA_UB_CASE
+    return set_error(GTA_ERR_UNSUPPORTED, "gta_umma_bench: D must be 64, 96 or 128");
+}
+
 }  // namespace gta

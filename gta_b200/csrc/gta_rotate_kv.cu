@@ -21,6 +21,12 @@ struct RotArgs {
     int v_transform;
 };
 
+// One warp owns 32 consecutive keys of the tile and walks the head row block type by block type (se3 chunks, then
+// so3, then so2) so that every instruction is type-uniform while lanes still cover contiguous 16-byte chunks.
+// K and V of the same (key, chunk) share the rep data, and kUnroll (key, chunk) items are loaded before the first
+// one is consumed: ~2*kUnroll 16-byte loads in flight per thread keep HBM busy at low occupancy cost.
+constexpr int kRotUnroll = 3;
+
 template <typename T>
 __global__ void __launch_bounds__(128) rotate_kv_kernel(const RotArgs a) {
     const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -29,42 +35,77 @@ __global__ void __launch_bounds__(128) rotate_kv_kernel(const RotArgs a) {
     const size_t tile_bytes = static_cast<size_t>(128) * a.D * 2;
     const size_t blob = (static_cast<size_t>(b) * a.H + h) * a.ntiles + tile;
     const int seg_n[4] = {a.hd.triv >> 3, a.hd.se3 >> 3, a.hd.so3 >> 3, a.hd.so2 >> 3};
+    const T* ksrc = reinterpret_cast<const T*>(a.k) + static_cast<int64_t>(b) * a.k_sb + static_cast<int64_t>(h) * a.k_sh;
+    const T* vsrc = reinterpret_cast<const T*>(a.v) + static_cast<int64_t>(b) * a.v_sb + static_cast<int64_t>(h) * a.v_sh;
+    uint8_t* kdst = a.ws_k + blob * tile_bytes;
+    uint8_t* vdst = a.ws_v + blob * tile_bytes;
 
+    int cbase = 0;
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-        const T* src = reinterpret_cast<const T*>(which ? a.v : a.k) +
-                       static_cast<int64_t>(b) * (which ? a.v_sb : a.k_sb) + static_cast<int64_t>(h) * (which ? a.v_sh : a.k_sh);
-        const int64_t st = which ? a.v_st : a.k_st;
-        uint8_t* dst = (which ? a.ws_v : a.ws_k) + blob * tile_bytes;
-        const bool rotate = (which == 0) || a.v_transform;
-        int cbase = 0;
+    for (int seg = 0; seg < 4; ++seg) {
+        const int n_t = seg_n[seg];
+        if (n_t == 0) continue;
+        // this warp's items of the segment: (row r, chunk cbase + c), item index it = r * n_t + c, it in [0, 32 n_t)
 #pragma unroll 1
-        for (int seg = 0; seg < 4; ++seg) {
-            const int n_t = seg_n[seg];
-            if (n_t == 0) continue;
-            const int items = 32 * n_t;
-#pragma unroll 1
-            for (int it = lane; it < items; it += 32) {
-                const int r = it / n_t;
-                const int c = cbase + (it - r * n_t);
-                const int row = warp * 32 + r;
-                const int t = tile * 128 + row;
-                float x[8];
+        for (int base = 0; base < n_t; base += kRotUnroll) {
+            RawChunk<T> rk[kRotUnroll], rv[kRotUnroll];
+            int row[kRotUnroll], ch[kRotUnroll];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = 0.f;
-                if (t < a.Tk) {
-                    load_chunk<T>(src + t * st + c * 8, x);
-                    if (rotate && seg > 0) {
-                        const int n = t / a.tpv;
-                        const size_t view = static_cast<size_t>(b) * a.Nk + n;
-                        apply_rep_chunk<kModeKV>(x, c, a.hd, a.se3_k + view * 16, a.so3_k + view * 34,
-                                                 a.so2_k + (static_cast<size_t>(b) * a.Tk + t) * a.C * 2, tc);
+            for (int u = 0; u < kRotUnroll; ++u) {
+                const int it = (base + u) * 32 + lane;
+                const int r = it / n_t;
+                ch[u] = cbase + (it - r * n_t);
+                row[u] = (base + u < n_t) ? warp * 32 + r : -1;
+                const int t = tile * 128 + row[u];
+                zero_raw(rk[u]); zero_raw(rv[u]);
+                if (row[u] >= 0 && t < a.Tk) {
+                    load_raw(ksrc + t * a.k_st + ch[u] * 8, rk[u]);
+                    load_raw(vsrc + t * a.v_st + ch[u] * 8, rv[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kRotUnroll; ++u) {
+                if (row[u] < 0) continue;
+                const int t = tile * 128 + row[u];
+                float xk[8], xv[8];
+                raw_to_f32(rk[u], xk);
+                raw_to_f32(rv[u], xv);
+                if (seg > 0 && t < a.Tk) {
+                    const size_t view = static_cast<size_t>(b) * a.Nk + t / a.tpv;
+                    const float* se3 = a.se3_k + view * 16;
+                    const float* so3 = a.so3_k + view * 34;
+                    const float* so2 = a.so2_k + (static_cast<size_t>(b) * a.Tk + t) * a.C * 2;
+                    if (seg == 1) {
+                        float M[16];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float4 q4 = __ldg(reinterpret_cast<const float4*>(se3) + i);
+                            M[4 * i] = q4.x; M[4 * i + 1] = q4.y; M[4 * i + 2] = q4.z; M[4 * i + 3] = q4.w;
+                        }
+                        se3_apply(xk, M, tc);
+                        if (a.v_transform) se3_apply(xv, M, tc);
+                    } else if (seg == 2) {
+                        float W[34];
+#pragma unroll
+                        for (int i = 0; i < 17; ++i) {
+                            float2 q2 = __ldg(reinterpret_cast<const float2*>(so3) + i);
+                            W[2 * i] = q2.x; W[2 * i + 1] = q2.y;
+                        }
+                        so3_apply<false>(xk, W);
+                        if (a.v_transform) so3_apply<false>(xv, W);
+                    } else {
+                        const So2Chunk sc = load_so2_chunk(so2, ch[u], a.hd);
+                        const float cs[8] = {sc.a.x, sc.a.y, sc.a.z, sc.a.w, sc.b.x, sc.b.y, sc.b.z, sc.b.w};
+                        so2_apply<false>(xk, cs);
+                        if (a.v_transform) so2_apply<false>(xv, cs);
                     }
                 }
-                *reinterpret_cast<uint4*>(dst + tile_sw64_offset(row, c)) = pack_chunk_bf16(x);
+                const uint32_t off = tile_sw64_offset(row[u], ch[u]);
+                *reinterpret_cast<uint4*>(kdst + off) = pack_chunk_bf16(xk);
+                *reinterpret_cast<uint4*>(vdst + off) = pack_chunk_bf16(xv);
             }
-            cbase += n_t;
         }
+        cbase += n_t;
     }
 }
 

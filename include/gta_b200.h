@@ -82,6 +82,8 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_STAGE_ONLY 4  /* launch only the K'/V' staging kernel (fills the workspace) */
 #define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 #define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
+#define GTA_FLAG_V3_PIPELINE 32 /* experiment: persistent CTAs with 64-key half tiles and double-buffered S (N=64 MMAs are
+                                   no cheaper than N=128 ones on sm_100a, so this is slower; kept for the record) */
 
 /* Scratch for the rotated K'/V' operand tiles. */
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D);
@@ -111,6 +113,9 @@ int gta_wigner_d(const float* R, int64_t n, float* d1, float* d2, void* stream);
  * outS [128,128], outO [128,D] fp32.  p_in_tmem selects the TS form for the PV product. */
 int gta_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem,
                    float* outS, float* outO, void* stream);
+
+/* tcgen05.mma issue/throughput micro-benchmark (tools/umma_bench.py): out[grid][2] = clocks (issue, issue+drain). */
+int gta_umma_bench(int D, int mode, int reps, int grid, long long* out, void* stream);
 
 const char* gta_last_error(void);
 int gta_abi_version(void);
