@@ -20,6 +20,7 @@ GTA_FLAG_STAGE_ONLY = 4
 GTA_FLAG_V0_PIPELINE = 8
 GTA_FLAG_V1_PIPELINE = 16
 GTA_FLAG_V3_PIPELINE = 32
+GTA_FLAG_V4_PIPELINE = 64
 
 
 class GtaReps(ctypes.Structure):
@@ -49,6 +50,7 @@ SYMBOLS = {
     "gta_wigner_d": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gta_umma_probe": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 3),
     "gta_umma_bench": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gta_softmax_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gta_last_error": (c_char_p, []),
     "gta_abi_version": (c_int, []),
 }

@@ -22,6 +22,11 @@ __device__ __forceinline__ uint64_t desc_p_sw128(uint32_t p_addr, int kk) {
     return make_smem_desc(p_addr + (kk >> 2) * 16384u + (kk & 3) * 32u, 16u, 1024u, kLayoutSW128);
 }
 
+// Low-word increments (16-byte units) of the K-step descriptors above, for the lean issue path.
+__device__ __forceinline__ constexpr uint32_t kstep_kmajor_sw64(int kk) { return (kk >> 1) * 512u + (kk & 1) * 2u; }
+__device__ __forceinline__ constexpr uint32_t kstep_mnmajor_sw64(int kk) { return kk * 64u; }
+__device__ __forceinline__ constexpr uint32_t kstep_p_sw128(int kk) { return (kk >> 2) * 1024u + (kk & 3) * 2u; }
+
 struct AttnArgs {
     const void* q;
     int64_t q_sb, q_sh, q_st;

@@ -28,6 +28,9 @@ int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v2(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v3(const GtaAttnParams& p, cudaStream_t st);
+int launch_attn_fwd_v4(const GtaAttnParams& p, cudaStream_t st);
+int launch_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
+                         cudaStream_t st);
 int launch_umma_bench(int D, int mode, int reps, int grid, long long* out, cudaStream_t st);
 int launch_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem, float* outS,
                       float* outO, cudaStream_t st);

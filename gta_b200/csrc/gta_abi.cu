@@ -115,4 +115,9 @@ int gta_umma_bench(int D, int mode, int reps, int grid, long long* out, void* st
     return launch_umma_bench(D, mode, reps, grid, out, static_cast<cudaStream_t>(stream));
 }
 
+int gta_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
+                      void* stream) {
+    return launch_softmax_bench(num, den, warps, reps, grid, in, out, clk, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

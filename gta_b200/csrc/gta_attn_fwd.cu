@@ -525,4 +525,51 @@ int launch_umma_bench(int D, int mode, int reps, int grid, long long* out, cudaS
     return set_error(GTA_ERR_UNSUPPORTED, "gta_umma_bench: D must be 64, 96 or 128");
 }
 
+
+// ===================================================================================================
+// Softmax inner-block micro-benchmark (tools/softmax_bench.py): the exp2 / row-sum / bf16-pack phase of one
+// 128-column score row per thread, repeated `reps` times, with POLY of every DEN pairs evaluated by poly_exp2x2.
+template <int NUM, int DEN>
+__global__ void softmax_bench_kernel(const float* __restrict__ in, float* __restrict__ out, int reps, long long* clk) {
+    float s[128];
+#pragma unroll
+    for (int i = 0; i < 128; ++i) s[i] = in[(threadIdx.x * 128 + i) & 1023];
+    const float cs = 0.1f, neg = -0.3f;
+    const uint64_t cs2 = pack_f32x2(cs, cs), neg2 = pack_f32x2(neg, neg);
+    uint32_t acc = 0;
+    uint64_t lsum2 = pack_f32x2(0.f, 0.f);
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            const uint64_t x2 = ffma2(pack_f32x2(s[2 * i], s[2 * i + 1]), cs2, neg2);
+            float p0, p1;
+            if ((i % DEN) < NUM) {
+                poly_exp2x2(x2, p0, p1);
+            } else {
+                float x0, x1;
+                unpack_f32x2(x2, x0, x1);
+                p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+            }
+            lsum2 = fadd2(lsum2, pack_f32x2(p0, p1));
+            acc ^= pack_bf16x2(p0, p1);
+            s[2 * i] = p0 - 1.0f;           // feed back so that the loop cannot be hoisted
+        }
+    }
+    const long long t1 = clock64();
+    float l0, l1;
+    unpack_f32x2(lsum2, l0, l1);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = l0 + l1 + __uint_as_float(acc);
+    if (threadIdx.x == 0) clk[blockIdx.x] = t1 - t0;
+}
+
+int launch_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
+                         cudaStream_t st) {
+#define GTA_SB(N_, D_) if (num == N_ && den == D_) { softmax_bench_kernel<N_, D_><<<grid, warps * 32, 0, st>>>(in, out, reps, clk); return check_launch("gta_softmax_bench"); }
+    GTA_SB(0, 4) GTA_SB(1, 4) GTA_SB(1, 3) GTA_SB(1, 2) GTA_SB(2, 3) GTA_SB(1, 1)
+#undef GTA_SB
+    return set_error(GTA_ERR_UNSUPPORTED, "gta_softmax_bench: unsupported poly fraction");
+}
+
 }  // namespace gta

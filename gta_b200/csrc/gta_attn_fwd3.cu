@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
         // optional phase clocks (GtaAttnParams.debug_clocks): [cta][16] accumulated over the CTA's items
         long long* dbg = (a.dbg && threadIdx.x == 0) ? a.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
         long long d_loop = 0, d_epi = 0, d_wait_s = 0, d_wait_o = 0, d_items = 0;
-        long long d_ld = 0, d_max = 0, d_exp = 0, d_st = 0;
+        long long d_e[4] = {0, 0, 0, 0};
         const long long d_start = dbg ? clock64() : 0;
 
 #pragma unroll 1
@@ -143,10 +143,21 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
 
 #pragma unroll 1
             for (int j = 0; j < n; ++j, ++gt) {
+                if (j == n - 1 && a.v_transform) {
+                    // pull this row's output-rotation operands into L1 one key tile before the epilogue needs them
+                    const int t_ = ic.p * 256 + X * 128 + r;
+                    const int tt_ = t_ < a.Tq ? t_ : a.Tq - 1;
+                    const size_t view_ = static_cast<size_t>(ic.b) * a.Nq + tt_ / a.tpvq;
+                    if (a.hd.se3) prefetch_l1(a.se3_q + view_ * 16);
+                    if (a.hd.so3) { prefetch_l1(a.so3_q + view_ * 34); prefetch_l1(a.so3_q + view_ * 34 + 32); }
+                    if (a.hd.so2) {
+                        const float* so2_ = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt_) * a.C * 2;
+                        for (int off = 0; off < a.C * 2; off += 32) prefetch_l1(so2_ + off);
+                    }
+                }
                 const long long d_w0 = dbg ? clock64() : 0;
                 mbar_wait(&bars[L::bSFull + X], gt & 1);
-                const long long d_p0 = dbg ? clock64() : 0;
-                if (dbg) d_wait_s += d_p0 - d_w0;
+                if (dbg) d_wait_s += clock64() - d_w0;
                 tc_fence_after();
                 uint32_t sreg[128];
                 tmem_ld32(s_addr, sreg);
@@ -154,7 +165,6 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                 tmem_ld32(s_addr + 64, sreg + 64);
                 tmem_ld32(s_addr + 96, sreg + 96);
                 tmem_ld_wait();
-                const long long d_p1 = dbg ? clock64() : 0;
                 float* s = reinterpret_cast<float*>(sreg);
                 if (j == n - 1) {
                     const int nvalid = a.Tk - j * 128;
@@ -192,7 +202,6 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                     }
                 }
 
-                const long long d_p2 = dbg ? clock64() : 0;
                 const float neg = -m_used * cs;
                 const uint64_t neg2 = pack_f32x2(neg, neg);
                 uint64_t lsum2 = pack_f32x2(0.f, 0.f);
@@ -219,13 +228,9 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                 float ls0, ls1;
                 unpack_f32x2(lsum2, ls0, ls1);
                 l_run += ls0 + ls1;
-                const long long d_p3 = dbg ? clock64() : 0;
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[L::bPFull + X]);
-                if (dbg) {
-                    d_ld += d_p1 - d_p0; d_max += d_p2 - d_p1; d_exp += d_p3 - d_p2; d_st += clock64() - d_p3;
-                }
             }
 
             // ---- epilogue of this item: prefetch the row's reps, drain O to registers, release O, then finish.
@@ -233,50 +238,116 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
             const int t = ic.p * 256 + X * 128 + r;
             const bool valid = t < a.Tq;
             const int tt = valid ? t : a.Tq - 1;
-            ViewReps vr;
+            // The output rotation walks the head row block type by block type with rolled loops (8 accumulator columns
+            // per step straight from TMEM), so only ONE kind of rep data is live at a time: the view matrices are requested
+            // before the wait for the last PV, the per-token SO(2) entries one chunk ahead of their use.  (A fully
+            // unrolled epilogue kept M, W and all SO(2) chunks live next to 96 accumulator values and spilled ~150
+            // local-memory loads per 32-column block.)
+            const int c_se3 = a.hd.triv >> 3, n_se3 = a.hd.se3 >> 3, c_so3 = c_se3 + n_se3, n_so3 = a.hd.so3 >> 3;
+            const int c_so2 = c_so3 + n_so3;
+            // (all of this row's rep data was pulled into L1 one key tile ago, so each block loads its operands right
+            //  before use and nothing has to stay live across the wait)
+            const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
             const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
-            if (a.v_transform) {
-                const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
-                load_view_reps(vr, a.hd, a.se3_q + view * 16, a.so3_q + view * 34);
-            }
             mbar_wait(&bars[L::bOFinal + X], cnt & 1);
             const long long d_t2 = dbg ? clock64() : 0;
             ++cnt;
             tc_fence_after();
-            uint32_t o[D];
-#pragma unroll
-            for (int cb = 0; cb < D / 32; ++cb) tmem_ld32(o_addr + cb * 32, o + cb * 32);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[L::bOFree + X]);          // the next item's PV_X(0) may overwrite O_X now
-
             const float inv_l = 1.0f / l_run;
             TOut* orow = reinterpret_cast<TOut*>(a.out) + ((static_cast<int64_t>(ic.b) * a.Tq + tt) * a.H + ic.h) * D;
+            // O columns are fetched 8 at a time, one chunk AHEAD of their use (tcgen05.ld is asynchronous until
+            // tcgen05.wait::ld), so the TMEM round trip overlaps the rotation of the previous chunk.
+            uint32_t ocur[8];
+            tmem_ld8(o_addr, ocur);
+            auto next_o = [&](int c, float* x) {          // returns chunk c (already in flight), starts chunk c + 1
+                tmem_ld_wait();
 #pragma unroll
-            for (int cp = 0; cp < D / 16; ++cp) {
-                So2Chunk sc[2];
+                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(ocur[i]) * inv_l;
+                if (c + 1 < D / 8) tmem_ld8(o_addr + (c + 1) * 8, ocur);   // consumed above; in-order issue makes the reuse safe
+            };
+            // 32-byte stores (STG.256): a thread owns a whole 2*D-byte output row, so every 16-byte store is its own
+            // L1/L2 transaction (the v2 epilogue was bound by ~2.5 clk per such transaction); pairing two chunks halves
+            // the transaction count and writes full sectors.  `pend` carries the even chunk across block-type sections.
+            uint4 pend = make_uint4(0, 0, 0, 0);
+            auto emit = [&](int c, const float* x) {
+                if (sizeof(TOut) == 4) {
+                    if (valid)
+                        st_global_v8(orow + c * 8, make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])),
+                                     make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7])));
+                } else {
+                    const uint4 pk = pack_chunk_bf16(x);
+                    if (c & 1) { if (valid) st_global_v8(orow + (c - 1) * 8, pend, pk); }
+                    else pend = pk;
+                }
+            };
+            const long long e0 = dbg ? clock64() : 0;
+            const int c_rot = a.v_transform ? c_se3 : D / 8;       // chunks below c_rot are stored as they are
+#pragma unroll 1
+            for (int c = 0; c < c_rot; ++c) {
+                float x[8];
+                next_o(c, x);
+                emit(c, x);
+            }
+            long long e1 = 0, e2 = 0;
+            if (a.v_transform) {
+                if (c_so3 > c_se3) {
+                    float M[16];
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) sc[cc] = load_so2_chunk(so2, cp * 2 + cc, a.hd);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 q4 = __ldg(reinterpret_cast<const float4*>(a.se3_q + view * 16) + i);
+                        M[4 * i] = q4.x; M[4 * i + 1] = q4.y; M[4 * i + 2] = q4.z; M[4 * i + 3] = q4.w;
+                    }
+#pragma unroll 1
+                    for (int c = c_se3; c < c_so3; ++c) {
+                        float x[8];
+                        next_o(c, x);
+                        se3_apply(x, M, tc);
+                        emit(c, x);
+                    }
+                }
+                if (dbg) e1 = clock64();
+                if (c_so2 > c_so3) {
+                    float W[34];
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = cp * 2 + cc;
+                    for (int i = 0; i < 17; ++i) {
+                        const float2 q2 = __ldg(reinterpret_cast<const float2*>(a.so3_q + view * 34) + i);
+                        W[2 * i] = q2.x; W[2 * i + 1] = q2.y;
+                    }
+#pragma unroll 1
+                    for (int c = c_so3; c < c_so2; ++c) {
+                        float x[8];
+                        next_o(c, x);
+                        so3_apply<true>(x, W);
+                        emit(c, x);
+                    }
+                }
+                if (dbg) e2 = clock64();
+                So2Chunk sc_cur = load_so2_chunk(so2, c_so2, a.hd);
+#pragma unroll 1
+                for (int c = c_so2; c < D / 8; ++c) {
+                    So2Chunk sc_nxt = sc_cur;
+                    if (c + 1 < D / 8) sc_nxt = load_so2_chunk(so2, c + 1, a.hd);
                     float x[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(o[c * 8 + i]) * inv_l;
-                    if (a.v_transform) apply_rep_chunk_pre<kModeOut>(x, c, a.hd, vr, sc[cc], tc);
-                    if (valid) store_chunk<TOut>(orow + c * 8, x);
+                    next_o(c, x);
+                    const float cs8[8] = {sc_cur.a.x, sc_cur.a.y, sc_cur.a.z, sc_cur.a.w, sc_cur.b.x, sc_cur.b.y, sc_cur.b.z, sc_cur.b.w};
+                    so2_apply<true>(x, cs8);
+                    emit(c, x);
+                    sc_cur = sc_nxt;
                 }
             }
+            tc_fence_before();
+            mbar_arrive(&bars[L::bOFree + X]);                  // O_X fully read: the next item's PV_X(0) may overwrite it
             if (a.lse && valid)
                 a.lse[(static_cast<int64_t>(ic.b) * a.H + ic.h) * a.Tq + t] = m_used * a.scale + logf(l_run);
             if (dbg) {
                 const long long d_t3 = clock64();
                 d_loop += d_t1 - d_t0; d_wait_o += d_t2 - d_t1; d_epi += d_t3 - d_t2; ++d_items;
+                d_e[0] += e0 - d_t2; d_e[1] += e1 - e0; d_e[2] += e2 - e1; d_e[3] += d_t3 - e2;
             }
         }
         if (dbg) {
             dbg[0] = clock64() - d_start; dbg[1] = d_loop; dbg[2] = d_epi; dbg[3] = d_wait_s; dbg[4] = d_wait_o;
-            dbg[5] = d_items; dbg[6] = d_ld; dbg[7] = d_max; dbg[13] = d_exp; dbg[14] = d_st;
+            dbg[5] = d_items; dbg[6] = d_e[0]; dbg[7] = d_e[1]; dbg[13] = d_e[2]; dbg[14] = d_e[3];
         }
     } else {
       setmaxnreg_dec<96>();
@@ -336,6 +407,7 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
             uint32_t gk = 0;                   // global key-tile counter of this CTA (K/V ring position)
             uint32_t gtx[2] = {0, 0};          // tiles per softmax warpgroup (p_full phase)
             uint32_t cntx[2] = {0, 0};         // items per tile slot (Q buffer / o_free phase)
+            const uint32_t bar0 = smem_u32(bars);
             long long* dbg = (a.dbg && lane == 0) ? a.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
             long long w_k = 0, w_v = 0, w_p = 0, w_of = 0, w_q = 0;
 #define GTA_TIMED_WAIT(acc, ...)                                 \
@@ -358,15 +430,18 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
 
                 auto issue_qk = [&](int X, int j) {
                     const int s = (gk + j) % NS;
-                    if (lane == 0) {
-                        const uint32_t k_addr = smem_u32(smem + L::kK + s * L::kTile);
+                    if (elect_one()) {
+                        const uint64_t qd = desc_kmajor_sw64(q_addr[X], 0);
+                        const uint64_t kd = desc_kmajor_sw64(smem_u32(smem + L::kK + s * L::kTile), 0);
+                        const uint32_t qlo = static_cast<uint32_t>(qd), qhi = static_cast<uint32_t>(qd >> 32);
+                        const uint32_t klo = static_cast<uint32_t>(kd), khi = static_cast<uint32_t>(kd >> 32);
                         const uint32_t d_addr = tmem_base + (X ? k3TmemSB : k3TmemSA);
 #pragma unroll
                         for (int kk = 0; kk < D / 16; ++kk)
-                            umma_ss(d_addr, desc_kmajor_sw64(q_addr[X], kk), desc_kmajor_sw64(k_addr, kk), idesc_qk, kk > 0);
-                        if (X == nx - 1) umma_commit(&bars[L::bKEmpty + s]);
-                        if (j == n - 1) umma_commit(&bars[L::bQFree + (cntx[X] & 1) * 2 + X]);
-                        umma_commit(&bars[L::bSFull + X]);
+                            umma_ss_lohi(d_addr, qlo + kstep_kmajor_sw64(kk), qhi, klo + kstep_kmajor_sw64(kk), khi, idesc_qk, kk > 0);
+                        if (X == nx - 1) umma_commit_addr(bar0 + (L::bKEmpty + s) * 8);
+                        if (j == n - 1) umma_commit_addr(bar0 + (L::bQFree + (cntx[X] & 1) * 2 + X) * 8);
+                        umma_commit_addr(bar0 + (L::bSFull + X) * 8);
                     }
                     __syncwarp();
                 };
@@ -375,16 +450,17 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                     GTA_TIMED_WAIT(w_p, mbar_wait(&bars[L::bPFull + X], (gtx[X] + j) & 1));
                     if (j == 0 && cntx[X] > 0) GTA_TIMED_WAIT(w_of, mbar_wait(&bars[L::bOFree + X], (cntx[X] - 1) & 1));
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t v_addr = smem_u32(smem + L::kV + s * L::kTile);
+                    if (elect_one()) {
+                        const uint64_t vd = desc_mnmajor_sw64(smem_u32(smem + L::kV + s * L::kTile), 0);
+                        const uint32_t vlo = static_cast<uint32_t>(vd), vhi = static_cast<uint32_t>(vd >> 32);
                         const uint32_t d_addr = tmem_base + (X ? k3TmemOB : k3TmemOA);
                         const uint32_t p_addr = tmem_base + (X ? k3TmemSB : k3TmemSA);
 #pragma unroll
                         for (int kk = 0; kk < 8; ++kk)
-                            umma_ts(d_addr, p_addr + kk * 8, desc_mnmajor_sw64(v_addr, kk), idesc_pv,
-                                    (j > 0 || kk > 0) ? 1u : 0u);
-                        if (X == nx - 1) umma_commit(&bars[L::bVEmpty + s]);
-                        if (j == n - 1) umma_commit(&bars[L::bOFinal + X]);
+                            umma_ts_lohi(d_addr, p_addr + kk * 8, vlo + kstep_mnmajor_sw64(kk), vhi, idesc_pv,
+                                         (j > 0 || kk > 0) ? 1u : 0u);
+                        if (X == nx - 1) umma_commit_addr(bar0 + (L::bVEmpty + s) * 8);
+                        if (j == n - 1) umma_commit_addr(bar0 + (L::bOFinal + X) * 8);
                     }
                     __syncwarp();
                 };

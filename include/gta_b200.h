@@ -82,6 +82,7 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_STAGE_ONLY 4  /* launch only the K'/V' staging kernel (fills the workspace) */
 #define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 #define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
+#define GTA_FLAG_V4_PIPELINE 64 /* experiment: persistent CTAs, S/P decoupled, one UMMA issuer warp per query tile */
 #define GTA_FLAG_V3_PIPELINE 32 /* experiment: persistent CTAs with 64-key half tiles and double-buffered S (N=64 MMAs are
                                    no cheaper than N=128 ones on sm_100a, so this is slower; kept for the record) */
 
@@ -116,6 +117,10 @@ int gta_umma_probe(const void* A, const void* Bm, const void* P, const void* V, 
 
 /* tcgen05.mma issue/throughput micro-benchmark (tools/umma_bench.py): out[grid][2] = clocks (issue, issue+drain). */
 int gta_umma_bench(int D, int mode, int reps, int grid, long long* out, void* stream);
+
+/* exp2/pack phase micro-benchmark (tools/softmax_bench.py): clk[grid] = clocks of `reps` 128-column rows per thread. */
+int gta_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
+                      void* stream);
 
 const char* gta_last_error(void);
 int gta_abi_version(void);

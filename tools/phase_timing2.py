@@ -17,7 +17,7 @@ def main():
     base, nq, nk, tq, tk, cross, B, _ = WORKLOADS[name]
     if len(sys.argv) > 2:
         B = int(sys.argv[2])
-    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk, v_transform=os.environ.get('V_TRANSFORM', '1') == '1')
     inp = make_inputs(cfg, B, tq, tk, cross=cross, seed=0, dtype=torch.bfloat16)
     dev = torch.device("cuda")
     ek, ck = inp["extr_k"].to(dev), inp["coord_k"].to(dev)
@@ -26,10 +26,11 @@ def main():
     reps = ops.build_reps(eq, ek, cq, ck, so2_nfreqs=cfg.so2, so3_maxdeg=cfg.so3)
     q, k, v = (inp[n].to(dev) for n in "qkv")
     tc = torch.tensor([0.01], device=dev)
+    flags = int(os.environ.get('GTA_FLAGS', '0'))
     for _ in range(3):
-        ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, flags=int(os.environ.get('GTA_FLAGS', '0')))
+        ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, v_transform=cfg.v_transform, flags=int(os.environ.get('GTA_FLAGS', '0')))
     dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
-    ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, debug_clocks=dbg, flags=int(os.environ.get('GTA_FLAGS', '0')))
+    ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, v_transform=cfg.v_transform, debug_clocks=dbg, flags=int(os.environ.get('GTA_FLAGS', '0')))
     torch.cuda.synchronize()
     d = dbg.cpu().double()
     d = d[d[:, 5] > 0]
@@ -41,9 +42,14 @@ def main():
         print(f"  {nme:28s} per item {(d[:,i]/items).mean():8.0f} clk  ({100*(d[:,i]/d[:,0]).mean():5.1f}% of span)")
     print(f"  per key tile: loop {(d[:,1]/items/ntile).mean():.0f} clk, of which s_full wait {(d[:,3]/items/ntile).mean():.0f};"
           f" tensor work per tile-pair {2*2*128*128*cfg.head_dim*2/8192:.0f} clk")
-    for i, nme in ((6, "tmem ld S + wait"), (7, "mask/max/rescale"), (13, "exp2 + pack + tmem st issue"), (14, "st wait + fence + arrive")):
-        print(f"  softmax phase {nme:30s} per key tile {(d[:,i]/items/ntile).mean():7.0f} clk")
-    for i, nme in ((8, "k_full"), (9, "v_full"), (10, "p_full"), (11, "o_free"), (12, "q_full")):
+    if flags == 64:
+        print(f"  v4: pv_done waits per key tile {(d[:,6]/items/ntile).mean():7.0f} clk")
+        for X, nm in ((0, "A"), (1, "B")):
+            print(f"  UMMA issuer {nm}: per key tile wait s_free {(d[:,8+3*X]/items/ntile).mean():6.0f}, p_full {(d[:,9+3*X]/items/ntile).mean():6.0f}, k/v_full {(d[:,10+3*X]/items/ntile).mean():6.0f} clk")
+    if flags != 64:
+        for i, nme in ((6, "setup (1/l, first tmem ld)"), (7, "triv+se3 chunks"), (13, "so3 chunks"), (14, "so2 chunks + o_free + lse")):
+            print(f"  epilogue part {nme:30s} per item {(d[:,i]/items).mean():7.0f} clk")
+    for i, nme in () if flags == 64 else ((8, "k_full"), (9, "v_full"), (10, "p_full"), (11, "o_free"), (12, "q_full")):
         print(f"  UMMA issuer wait on {nme:7s} per item {(d[:,i]/items).mean():8.0f} clk ({100*(d[:,i]/d[:,0]).mean():5.1f}% of span)")
 
 
