@@ -19,7 +19,6 @@ GTA_FLAG_SKIP_STAGE = 2
 GTA_FLAG_STAGE_ONLY = 4
 GTA_FLAG_V0_PIPELINE = 8
 GTA_FLAG_V1_PIPELINE = 16
-GTA_FLAG_V3_PIPELINE = 32
 GTA_FLAG_V4_PIPELINE = 64
 
 

@@ -373,8 +373,8 @@ static int launch2_d(const AttnArgs& a, int D, dim3 grid, cudaStream_t st) {
 
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st) {
     if (p.flags & GTA_FLAG_V0_PIPELINE) return launch_attn_fwd_v0(p, st);
-    if ((p.flags & GTA_FLAG_V3_PIPELINE) && p.D <= 96) return launch_attn_fwd_v3(p, st);   // 64-key S tiles (slower: see DESIGN.md)
-    if ((p.flags & GTA_FLAG_V4_PIPELINE) && p.D <= 96) return launch_attn_fwd_v4(p, st);   // experiment: S/P decoupled
+    if ((p.flags & GTA_FLAG_V4_PIPELINE) && p.D <= 96 && ((p.Tq + 127) / 128) % 2 == 0)
+        return launch_attn_fwd_v4(p, st);                                                   // S/P decoupled (needs tile pairs)
     if (!(p.flags & GTA_FLAG_V1_PIPELINE) && p.D <= 96) return launch_attn_fwd_v2(p, st);  // default: persistent pipeline
     const AttnArgs a = make_attn_args(p);
     dim3 grid((p.Tq + 255) / 256, p.H, p.B);

@@ -6,13 +6,16 @@
 // and the UMMA issuer waited ~28 % of the time for P.  Here:
 //   * the softmax warpgroup releases S_X as soon as it has been copied to registers (s_free) and QK_X(j+1) is issued
 //     right then, overlapping the exp2 phase;
-//   * P no longer aliases S: P_A lives in the last 64 TMEM columns (TS form), P_B in shared memory (SS form,
-//     128-byte swizzle) — TMEM is exactly full: S_A S_B 256 + O_A O_B 192 + P_A 64 = 512 columns;
+//   * P no longer aliases S: ONE P buffer in the last 64 TMEM columns is shared by both query tiles in strict
+//     alternation (their softmax phases are offset by half a cycle anyway) — TMEM is exactly full:
+//     S_A S_B 256 + O_A O_B 192 + P 64 = 512 columns; both PV products use the TS form;
 //   * each query tile has its OWN UMMA issuer warp running the stream [s_free(j) -> QK(j+1)] [p_full(j) -> PV(j)]
 //     with blocking waits on its own barriers, so a slow tile never blocks the other (a single polling issuer was
 //     tried first: mbarrier.test_wait costs ~150 clk and the serial event loop became the bottleneck);
 //   * K'/V' stages are released by BOTH streams (k_empty/v_empty count 2), PV completion is published per tile
-//     (pv_done) for the P-buffer reuse and the lazy accumulator rescale.
+//     (pv_done) for the lazy accumulator rescale and (p_free) for the shared P buffer.
+// The launcher only selects this kernel when every work item has both query tiles (ceil(Tq/128) even); other shapes
+// run the v2 pipeline.
 //
 //   warps 0-3 / 4-7  softmax warpgroups A / B (thread i <-> query row i <-> TMEM lane i), also run the epilogue
 //   warps 8 / 9      UMMA issuers of tile A / B      warp 10   bulk-copy producer (2-stage K'/V' ring)
@@ -45,8 +48,7 @@ struct Attn5Cfg {
     static constexpr uint32_t kQ = 0;                          // [2 buffers][2 tiles]
     static constexpr uint32_t kK = 4 * kTile;                  // [kStages]
     static constexpr uint32_t kV = kTile * (4 + kStages);      // [kStages]
-    static constexpr uint32_t kPB = kTile * (4 + 2 * kStages); // P of tile B, 32 KB
-    static constexpr uint32_t kBars = kPB + 32768u;
+    static constexpr uint32_t kBars = kTile * (4 + 2 * kStages);
     enum : int {
         bQFull = 0,                        // [qbuf][X]  count 64 (stager threads)
         bQFree = 4,                        // [qbuf][X]  commit after the item's last QK_X
@@ -60,11 +62,12 @@ struct Attn5Cfg {
         bPVDone = bPFull + 2,              // [X] commit after every PV_X
         bOFinal = bPVDone + 2,             // [X] commit after the item's last PV_X
         bOFree = bOFinal + 2,              // [X] count 128: O_X read out
-        bCount = bOFree + 2
+        bPFree = bOFree + 2,               // commit after every PV (either stream): the shared P buffer may be rewritten
+        bCount = bPFree + 1
     };
     static constexpr uint32_t kTmemSlot = kBars + bCount * 8;
     static constexpr uint32_t kUsed = kTmemSlot + 16;
-    static constexpr uint32_t kBytes = kUsed + 1024;
+    static constexpr uint32_t kBytes = (kUsed + 1024 > 120u * 1024u) ? kUsed + 1024 : 120u * 1024u;
 };
 
 struct Item5 {
@@ -106,6 +109,7 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_fwd5_kernel(const AttnArgs 
             mbar_init(&bars[L::bOFinal + x], 1);
             mbar_init(&bars[L::bOFree + x], 128);
         }
+        mbar_init(&bars[L::bPFree], 1);
         for (int s = 0; s < NS; ++s) {
             mbar_init(&bars[L::bKFull + s], 1);
             mbar_init(&bars[L::bVFull + s], 1);
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_fwd5_kernel(const AttnArgs 
         const uint32_t s_addr = lane_base + k5TmemS + X * 128;
         const uint32_t o_addr = lane_base + k5TmemO + X * 96;
         const uint32_t pa_addr = lane_base + k5TmemPA;
-        uint8_t* sPB = smem + L::kPB;
+        uint32_t T0 = 0;       // CTA-global index of the current item's first key tile (items without a B tile count too)
         const float cs = a.scale_log2;
         const uint64_t cs2 = pack_f32x2(cs, cs);
         uint32_t gt = 0;      // key tiles processed by this warpgroup (s_full / s_free / p_full / pv_done phases)
@@ -145,12 +149,26 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_fwd5_kernel(const AttnArgs 
 #pragma unroll 1
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const Item5 ic = decode_item5(item, npairs, a.H, a.Tq);
+            const uint32_t Tbase = T0;
+            T0 += n;
             if (X == 1 && !ic.has_b) continue;
             float m_used = -INFINITY, l_run = 0.f;
             const long long d_t0 = dbg ? clock64() : 0;
 
 #pragma unroll 1
             for (int j = 0; j < n; ++j, ++gt) {
+                if (j == n - 1 && a.v_transform) {
+                    // pull this row's output-rotation operands into L1 one key tile before the epilogue needs them
+                    const int t_ = ic.p * 256 + X * 128 + r;
+                    const int tt_ = t_ < a.Tq ? t_ : a.Tq - 1;
+                    const size_t view_ = static_cast<size_t>(ic.b) * a.Nq + tt_ / a.tpvq;
+                    if (a.hd.se3) prefetch_l1(a.se3_q + view_ * 16);
+                    if (a.hd.so3) { prefetch_l1(a.so3_q + view_ * 34); prefetch_l1(a.so3_q + view_ * 34 + 32); }
+                    if (a.hd.so2) {
+                        const float* so2_ = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt_) * a.C * 2;
+                        for (int off = 0; off < a.C * 2; off += 32) prefetch_l1(so2_ + off);
+                    }
+                }
                 const long long d_w0 = dbg ? clock64() : 0;
                 mbar_wait(&bars[L::bSFull + X], gt & 1);
                 if (dbg) d_wait_s += clock64() - d_w0;
@@ -226,68 +244,126 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_fwd5_kernel(const AttnArgs 
                         lsum2 = fadd2(lsum2, pack_f32x2(p0, p1));
                         sreg[half * 64 + i] = pack_bf16x2(p0, p1);      // in place (pair i is consumed before slot i)
                     }
-                    if (X == 0) {
-                        tmem_st32(pa_addr + half * 32, sreg + half * 64);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            *reinterpret_cast<uint4*>(sPB + tile_sw128_offset(r, half * 8 + c)) =
-                                make_uint4(sreg[half * 64 + 4 * c], sreg[half * 64 + 4 * c + 1], sreg[half * 64 + 4 * c + 2],
-                                           sreg[half * 64 + 4 * c + 3]);
-                    }
                 }
                 float ls0, ls1;
                 unpack_f32x2(lsum2, ls0, ls1);
                 l_run += ls0 + ls1;
-                if (X == 0) {
-                    tmem_st_wait();
-                } else {
-                    fence_proxy_async_smem();
+                // The ONE P buffer (64 TMEM columns) is shared by both query tiles in strict alternation
+                // A(T) B(T) A(T+1) B(T+1) ...: use u = 2T + X waits until the PV product of use u-1 has consumed it
+                // (for items without a B tile the B issuer passes the turn on).  This warpgroup's own previous use u-2
+                // is already known complete through pv_done, so the parity wait is unambiguous.
+                const uint32_t u = 2 * (Tbase + j) + X;
+                if (u > 0) {
+                    mbar_wait(&bars[L::bPFree], (u - 1) & 1);
+                    tc_fence_after();
                 }
+                tmem_st32(pa_addr, sreg);
+                tmem_st32(pa_addr + 32, sreg + 64);
+                tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(&bars[L::bPFull + X]);
             }
 
-            // ---- epilogue of this item.  Everything it needs from global memory is requested BEFORE waiting for the
-            // last PV: the view matrices and the row's SO(2) table.
+            // ---- epilogue of this item: prefetch the row's reps, drain O to registers, release O, then finish.
             const long long d_t1 = dbg ? clock64() : 0;
             const int t = ic.p * 256 + X * 128 + r;
             const bool valid = t < a.Tq;
             const int tt = valid ? t : a.Tq - 1;
-            ViewReps vr;
-            So2Chunk sc[D / 8];
-            if (a.v_transform) {
-                const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
-                load_view_reps(vr, a.hd, a.se3_q + view * 16, a.so3_q + view * 34);
-                const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
-#pragma unroll
-                for (int c = 0; c < D / 8; ++c) sc[c] = load_so2_chunk(so2, c, a.hd);
-            }
+            // The output rotation walks the head row block type by block type with rolled loops (8 accumulator columns
+            // per step straight from TMEM), so only ONE kind of rep data is live at a time: the view matrices are requested
+            // before the wait for the last PV, the per-token SO(2) entries one chunk ahead of their use.  (A fully
+            // unrolled epilogue kept M, W and all SO(2) chunks live next to 96 accumulator values and spilled ~150
+            // local-memory loads per 32-column block.)
+            const int c_se3 = a.hd.triv >> 3, n_se3 = a.hd.se3 >> 3, c_so3 = c_se3 + n_se3, n_so3 = a.hd.so3 >> 3;
+            const int c_so2 = c_so3 + n_so3;
+            // (all of this row's rep data was pulled into L1 one key tile ago, so each block loads its operands right
+            //  before use and nothing has to stay live across the wait)
+            const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
+            const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
             mbar_wait(&bars[L::bOFinal + X], cnt & 1);
             const long long d_t2 = dbg ? clock64() : 0;
             ++cnt;
             tc_fence_after();
             const float inv_l = 1.0f / l_run;
             TOut* orow = reinterpret_cast<TOut*>(a.out) + ((static_cast<int64_t>(ic.b) * a.Tq + tt) * a.H + ic.h) * D;
-#pragma unroll
-            for (int cb = 0; cb < D / 32; ++cb) {
-                uint32_t o[32];
-                tmem_ld32(o_addr + cb * 32, o);
+            // O columns are fetched 8 at a time, one chunk AHEAD of their use (tcgen05.ld is asynchronous until
+            // tcgen05.wait::ld), so the TMEM round trip overlaps the rotation of the previous chunk.
+            uint32_t ocur[8];
+            tmem_ld8(o_addr, ocur);
+            auto next_o = [&](int c, float* x) {          // returns chunk c (already in flight), starts chunk c + 1
                 tmem_ld_wait();
-                if (cb == D / 32 - 1) {                       // O_X fully read: the next item's PV_X(0) may overwrite it
-                    tc_fence_before();
-                    mbar_arrive(&bars[L::bOFree + X]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(ocur[i]) * inv_l;
+                if (c + 1 < D / 8) tmem_ld8(o_addr + (c + 1) * 8, ocur);   // consumed above; in-order issue makes the reuse safe
+            };
+            // 32-byte stores (STG.256): a thread owns a whole 2*D-byte output row, so every 16-byte store is its own
+            // L1/L2 transaction (the v2 epilogue was bound by ~2.5 clk per such transaction); pairing two chunks halves
+            // the transaction count and writes full sectors.  `pend` carries the even chunk across block-type sections.
+            uint4 pend = make_uint4(0, 0, 0, 0);
+            auto emit = [&](int c, const float* x) {
+                if (sizeof(TOut) == 4) {
+                    if (valid)
+                        st_global_v8(orow + c * 8, make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])),
+                                     make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7])));
+                } else {
+                    const uint4 pk = pack_chunk_bf16(x);
+                    if (c & 1) { if (valid) st_global_v8(orow + (c - 1) * 8, pend, pk); }
+                    else pend = pk;
                 }
+            };
+            const int c_rot = a.v_transform ? c_se3 : D / 8;       // chunks below c_rot are stored as they are
+#pragma unroll 1
+            for (int c = 0; c < c_rot; ++c) {
+                float x[8];
+                next_o(c, x);
+                emit(c, x);
+            }
+            if (a.v_transform) {
+                if (c_so3 > c_se3) {
+                    float M[16];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int c = cb * 4 + cc;
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 q4 = __ldg(reinterpret_cast<const float4*>(a.se3_q + view * 16) + i);
+                        M[4 * i] = q4.x; M[4 * i + 1] = q4.y; M[4 * i + 2] = q4.z; M[4 * i + 3] = q4.w;
+                    }
+#pragma unroll 1
+                    for (int c = c_se3; c < c_so3; ++c) {
+                        float x[8];
+                        next_o(c, x);
+                        se3_apply(x, M, tc);
+                        emit(c, x);
+                    }
+                }
+                if (c_so2 > c_so3) {
+                    float W[34];
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) {
+                        const float2 q2 = __ldg(reinterpret_cast<const float2*>(a.so3_q + view * 34) + i);
+                        W[2 * i] = q2.x; W[2 * i + 1] = q2.y;
+                    }
+#pragma unroll 1
+                    for (int c = c_so3; c < c_so2; ++c) {
+                        float x[8];
+                        next_o(c, x);
+                        so3_apply<true>(x, W);
+                        emit(c, x);
+                    }
+                }
+                So2Chunk sc_cur = load_so2_chunk(so2, c_so2, a.hd);
+#pragma unroll 1
+                for (int c = c_so2; c < D / 8; ++c) {
+                    So2Chunk sc_nxt = sc_cur;
+                    if (c + 1 < D / 8) sc_nxt = load_so2_chunk(so2, c + 1, a.hd);
                     float x[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(o[cc * 8 + i]) * inv_l;
-                    if (a.v_transform) apply_rep_chunk_pre<kModeOut>(x, c, a.hd, vr, sc[c], tc);
-                    if (valid) store_chunk<TOut>(orow + c * 8, x);
+                    next_o(c, x);
+                    const float cs8[8] = {sc_cur.a.x, sc_cur.a.y, sc_cur.a.z, sc_cur.a.w, sc_cur.b.x, sc_cur.b.y, sc_cur.b.z, sc_cur.b.w};
+                    so2_apply<true>(x, cs8);
+                    emit(c, x);
+                    sc_cur = sc_nxt;
                 }
             }
+            tc_fence_before();
+            mbar_arrive(&bars[L::bOFree + X]);                  // O_X fully read: the next item's PV_X(0) may overwrite it
             if (a.lse && valid)
                 a.lse[(static_cast<int64_t>(ic.b) * a.H + ic.h) * a.Tq + t] = m_used * a.scale + logf(l_run);
             if (dbg) {
@@ -359,8 +435,6 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_fwd5_kernel(const AttnArgs 
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
             const uint32_t bar0 = smem_u32(bars);
             const uint32_t q_base = smem_u32(smem + L::kQ), k_base = smem_u32(smem + L::kK), v_base = smem_u32(smem + L::kV);
-            const uint64_t pd = desc_p_sw128(smem_u32(smem + L::kPB), 0);
-            const uint32_t plo = static_cast<uint32_t>(pd), phi = static_cast<uint32_t>(pd >> 32);
             const uint32_t s_tmem = tmem_base + k5TmemS + X * 128, o_tmem = tmem_base + k5TmemO + X * 96;
             uint32_t T = 0;        // CTA-global key tile index (K/V ring position)
             uint32_t gt = 0;       // key tiles this stream has processed (s_free / p_full phases)
@@ -396,9 +470,9 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_fwd5_kernel(const AttnArgs 
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk) {
                         const uint32_t acc = (j > 0 || kk > 0) ? 1u : 0u;
-                        if (X == 0) umma_ts_lohi(o_tmem, tmem_base + k5TmemPA + kk * 8, vlo + kstep_mnmajor_sw64(kk), vhi, idesc_pv, acc);
-                        else umma_ss_lohi(o_tmem, plo + kstep_p_sw128(kk), phi, vlo + kstep_mnmajor_sw64(kk), vhi, idesc_pv, acc);
+                        umma_ts_lohi(o_tmem, tmem_base + k5TmemPA + kk * 8, vlo + kstep_mnmajor_sw64(kk), vhi, idesc_pv, acc);
                     }
+                    umma_commit_addr(bar0 + L::bPFree * 8);
                     umma_commit_addr(bar0 + (L::bVEmpty + s) * 8);
                     umma_commit_addr(bar0 + (L::bPVDone + X) * 8);
                     if (j == n - 1) umma_commit_addr(bar0 + (L::bOFinal + X) * 8);
@@ -409,18 +483,6 @@ __global__ void __launch_bounds__(kThreads5, 1) attn_fwd5_kernel(const AttnArgs 
 #pragma unroll 1
             for (int item = blockIdx.x; item < nitems; item += gridDim.x, T += n) {
                 const Item5 ic = decode_item5(item, npairs, a.H, a.Tq);
-                if (X == 1 && !ic.has_b) {
-                    // no B tile in this item: stay in step with the ring and release every stage unused
-#pragma unroll 1
-                    for (int j = 0; j < n; ++j) {
-                        const int s = (T + j) % NS;
-                        mbar_wait(&bars[L::bKFull + s], ((T + j) / NS) & 1);
-                        mbar_wait(&bars[L::bVFull + s], ((T + j) / NS) & 1);
-                        if (lane == 0) { mbar_arrive(&bars[L::bKEmpty + s]); mbar_arrive(&bars[L::bVEmpty + s]); }
-                        __syncwarp();
-                    }
-                    continue;
-                }
                 const uint64_t qd = desc_kmajor_sw64(q_base + ((cnt & 1) * 2 + X) * L::kTile, 0);
                 const uint32_t qlo = static_cast<uint32_t>(qd), qhi = static_cast<uint32_t>(qd >> 32);
                 mbar_wait(&bars[L::bQFull + (cnt & 1) * 2 + X], (cnt >> 1) & 1);

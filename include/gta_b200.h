@@ -83,8 +83,6 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 #define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
 #define GTA_FLAG_V4_PIPELINE 64 /* experiment: persistent CTAs, S/P decoupled, one UMMA issuer warp per query tile */
-#define GTA_FLAG_V3_PIPELINE 32 /* experiment: persistent CTAs with 64-key half tiles and double-buffered S (N=64 MMAs are
-                                   no cheaper than N=128 ones on sm_100a, so this is slower; kept for the record) */
 
 /* Scratch for the rotated K'/V' operand tiles. */
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D);
