@@ -50,6 +50,19 @@ def peaks():
     return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def traffic_bytes(workload, batch):
+    """DRAM bytes (read + write) of one launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r01_traffic.json); null when no capture exists for this workload/batch."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        t = json.load(open(p))
+        if t["workload"] == workload and t["batch_per_gpu"] == batch:
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler(threading.Thread):
     """SM clock and throttle reasons sampled DURING the timed region through NVML (in-process, ~2 ms period;
     falls back to polling nvidia-smi when pynvml is unavailable)."""
@@ -361,8 +374,8 @@ def main():
                            if in_bytes > 126e6 else "inputs %.0f MB fit L2; not flushed" % (in_bytes / 1e6),
                            p_operand="tmem" if args.flags & 1 else "smem"),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
-                         "kernel": "attn_fwd_kernel", "kernel_ms": ms_attn, "stage_kernel_ms": ms_stage,
+                         "frac": achieved / peak, "traffic": traffic_bytes(args.workload, B),
+                         "kernel": "attn_fwd3_kernel", "kernel_ms": ms_attn, "stage_kernel_ms": ms_stage,
                          "flops_per_launch": flops, "peak_source": pk_src +
                          (" burst" if total_s < 2.0 else " sustained")},
             "gpu_launches": launches_per_step * args.steps,
