@@ -18,6 +18,7 @@ GTA_FLAG_P_IN_TMEM = 1
 GTA_FLAG_SKIP_STAGE = 2
 GTA_FLAG_STAGE_ONLY = 4
 GTA_FLAG_V0_PIPELINE = 8
+GTA_FLAG_FAST_FP32 = 128
 GTA_FLAG_V1_PIPELINE = 16
 GTA_FLAG_V4_PIPELINE = 64
 
@@ -42,6 +43,7 @@ class GtaAttnParams(ctypes.Structure):
 # every symbol include/gta_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "gta_attn_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gta_attn_fwd_workspace_bytes_ex": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "gta_attn_fwd": (c_int, [POINTER(GtaAttnParams), c_void_p]),
     "gta_rotate_debug": (c_int, [POINTER(GtaAttnParams), c_void_p, c_void_p, c_void_p, c_void_p]),
     "gta_build_reps": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_float, c_float, c_int, c_int] + [c_void_p] * 7),

@@ -34,6 +34,13 @@ int launch_umma_bench(int D, int mode, int reps, int grid, long long* out, cudaS
 int launch_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem, float* outS,
                       float* outO, cudaStream_t st);
 
+// fp32 inputs run the split-precision pipeline (bf16 hi + bf16 residual operands, 3 MMAs per product term) unless the
+// caller asks for plain bf16 math with GTA_FLAG_FAST_FP32.
+inline bool attn_is_split_precision(const GtaAttnParams& p) {
+    return p.in_dtype == GTA_DTYPE_F32 && !(p.flags & GTA_FLAG_FAST_FP32);
+}
+int launch_attn_fwd_hp(const GtaAttnParams& p, cudaStream_t st);
+
 // Scratch layout: [K' tiles | V' tiles], each tile image = D/32 column blocks x 128 rows x 64 B (bf16).
 inline int num_kv_tiles(int Tk) { return (Tk + 127) / 128; }
 inline size_t kv_tile_bytes(int D) { return static_cast<size_t>(128) * D * 2; }

@@ -66,12 +66,17 @@ size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D) {
     return 2 * static_cast<size_t>(B) * H * num_kv_tiles(Tk) * kv_tile_bytes(D);
 }
 
+size_t gta_attn_fwd_workspace_bytes_ex(int B, int H, int Tk, int D, int in_dtype, int flags) {
+    const size_t base = gta_attn_fwd_workspace_bytes(B, H, Tk, D);
+    return (in_dtype == GTA_DTYPE_F32 && !(flags & GTA_FLAG_FAST_FP32)) ? 2 * base : base;
+}
+
 int gta_attn_fwd(const GtaAttnParams* p, void* stream) {
     int rc = validate_attn_params(p);
     if (rc) return rc;
-    if (!p->workspace || p->workspace_bytes < gta_attn_fwd_workspace_bytes(p->B, p->H, p->Tk, p->D))
-        return set_error(GTA_ERR_INVALID, "workspace too small (need %zu bytes)",
-                         gta_attn_fwd_workspace_bytes(p->B, p->H, p->Tk, p->D));
+    const size_t need = gta_attn_fwd_workspace_bytes_ex(p->B, p->H, p->Tk, p->D, p->in_dtype, p->flags);
+    if (!p->workspace || p->workspace_bytes < need)
+        return set_error(GTA_ERR_INVALID, "workspace too small (need %zu bytes)", need);
     if (reinterpret_cast<uintptr_t>(p->workspace) & 1023) return set_error(GTA_ERR_INVALID, "workspace must be 1024-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (!(p->flags & GTA_FLAG_SKIP_STAGE)) {
@@ -79,6 +84,7 @@ int gta_attn_fwd(const GtaAttnParams* p, void* stream) {
         if (rc) return rc;
     }
     if (p->flags & GTA_FLAG_STAGE_ONLY) return GTA_OK;
+    if (attn_is_split_precision(*p)) return launch_attn_fwd_hp(*p, st);
     return launch_attn_fwd(*p, st);
 }
 

@@ -19,7 +19,17 @@ struct RotArgs {
     const float* tc_ptr;
     int C;            // so2 pairs per token
     int v_transform;
+    size_t lo_offset; // split-precision mode: byte offset from a hi tile image to its lo (residual) image, else 0
 };
+
+// x -> bf16 hi part and bf16 residual (x - hi): hi + lo carries ~16 mantissa bits (fp32-accurate mode)
+__device__ __forceinline__ void split_chunk_bf16(const float* x, uint4& hi, uint4& lo) {
+    hi = pack_chunk_bf16(x);
+    float r[8];
+    r[0] = x[0] - bf16_lo(hi.x); r[1] = x[1] - bf16_hi(hi.x); r[2] = x[2] - bf16_lo(hi.y); r[3] = x[3] - bf16_hi(hi.y);
+    r[4] = x[4] - bf16_lo(hi.z); r[5] = x[5] - bf16_hi(hi.z); r[6] = x[6] - bf16_lo(hi.w); r[7] = x[7] - bf16_hi(hi.w);
+    lo = pack_chunk_bf16(r);
+}
 
 // One warp owns 32 consecutive keys of the tile and walks the head row block type by block type (se3 chunks, then
 // so3, then so2) so that every instruction is type-uniform while lanes still cover contiguous 16-byte chunks.
@@ -101,8 +111,18 @@ __global__ void __launch_bounds__(128) rotate_kv_kernel(const RotArgs a) {
                     }
                 }
                 const uint32_t off = tile_sw64_offset(row[u], ch[u]);
-                *reinterpret_cast<uint4*>(kdst + off) = pack_chunk_bf16(xk);
-                *reinterpret_cast<uint4*>(vdst + off) = pack_chunk_bf16(xv);
+                if (a.lo_offset) {
+                    uint4 hi, lo;
+                    split_chunk_bf16(xk, hi, lo);
+                    *reinterpret_cast<uint4*>(kdst + off) = hi;
+                    *reinterpret_cast<uint4*>(kdst + a.lo_offset + off) = lo;
+                    split_chunk_bf16(xv, hi, lo);
+                    *reinterpret_cast<uint4*>(vdst + off) = hi;
+                    *reinterpret_cast<uint4*>(vdst + a.lo_offset + off) = lo;
+                } else {
+                    *reinterpret_cast<uint4*>(kdst + off) = pack_chunk_bf16(xk);
+                    *reinterpret_cast<uint4*>(vdst + off) = pack_chunk_bf16(xv);
+                }
             }
         }
         cbase += n_t;
@@ -153,8 +173,11 @@ int launch_rotate_kv(const GtaAttnParams& p, cudaStream_t st) {
     a.v_sb = p.v_stride_b; a.v_sh = p.v_stride_h; a.v_st = p.v_stride_t;
     a.ntiles = num_kv_tiles(p.Tk);
     const size_t half = static_cast<size_t>(p.B) * p.H * a.ntiles * kv_tile_bytes(p.D);
+    const bool hp = attn_is_split_precision(p);
+    // workspace: [K' | V'] or, in split-precision mode, [K'hi | K'lo | V'hi | V'lo]
     a.ws_k = static_cast<uint8_t*>(p.workspace);
-    a.ws_v = a.ws_k + half;
+    a.ws_v = a.ws_k + (hp ? 2 * half : half);
+    a.lo_offset = hp ? half : 0;
     a.H = p.H; a.Tk = p.Tk; a.D = p.D; a.Nk = p.Nk; a.tpv = p.Tk / p.Nk;
     a.hd = HeadDims{p.triv, p.se3, p.so3, p.so2};
     a.se3_k = p.reps.se3_k; a.so3_k = p.reps.so3_k; a.so2_k = p.reps.so2_k;

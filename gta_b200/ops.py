@@ -126,7 +126,7 @@ def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: P
     out = torch.empty(B, Tq, H, D, device=dev, dtype=out_dtype or q.dtype)
     lse = torch.empty(B, H, Tq, device=dev, dtype=torch.float32) if return_lse else None
     p = _params(q, k, v, out, reps, f_dims, trans_coeff, scale, v_transform, flags, lse)
-    nbytes = lib().gta_attn_fwd_workspace_bytes(B, H, k.shape[2], D)
+    nbytes = lib().gta_attn_fwd_workspace_bytes_ex(B, H, k.shape[2], D, p.in_dtype, p.flags)
     ws = _workspace(dev, nbytes)
     base = ws.data_ptr()
     p.workspace = (base + 1023) // 1024 * 1024

@@ -69,7 +69,8 @@ typedef struct GtaAttnParams {
     GtaReps reps;
     const float* trans_coeff;  /* DEVICE pointer to the layer's scalar parameter (layers.py:188-191); NULL => 1.0 */
     float scale;               /* attn_fn.scale / tau  (layers.py:209) */
-    int in_dtype, out_dtype;   /* GTA_DTYPE_* */
+    int in_dtype, out_dtype;   /* GTA_DTYPE_*.  bf16 in: bf16 tensor-core math, 1e-2 parity budget.  f32 in: split-precision
+                                  (bf16 hi + residual, fp32 accumulation), 1e-3 budget, ~3x the tensor work. */
     int v_transform;           /* gta.py:156,168,277 */
     void* workspace;           /* >= gta_attn_fwd_workspace_bytes(...) bytes, 1024-byte aligned */
     size_t workspace_bytes;
@@ -80,12 +81,15 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_P_IN_TMEM 1   /* (v0 pipeline only) P operand of the PV MMA read from tensor memory */
 #define GTA_FLAG_SKIP_STAGE 2  /* workspace already holds K'/V' of these inputs: launch only the attention kernel */
 #define GTA_FLAG_STAGE_ONLY 4  /* launch only the K'/V' staging kernel (fills the workspace) */
+#define GTA_FLAG_FAST_FP32 128 /* fp32 inputs: multiply in plain bf16 (1e-2 budget) instead of the split-precision path */
 #define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 #define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
 #define GTA_FLAG_V4_PIPELINE 64 /* experiment: persistent CTAs, S/P decoupled, one UMMA issuer warp per query tile */
 
-/* Scratch for the rotated K'/V' operand tiles. */
+/* Scratch for the rotated K'/V' operand tiles (bf16 inputs, or fp32 inputs with GTA_FLAG_FAST_FP32). */
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D);
+/* Same for any dtype/flags: fp32 inputs use split-precision (hi + residual) tile images, twice the size. */
+size_t gta_attn_fwd_workspace_bytes_ex(int B, int H, int Tk, int D, int in_dtype, int flags);
 
 /* Fused forward: O = rho_q^{-1} softmax((rho_q^{-T} Q)(rho_k K)^T * scale) (rho_k V). */
 int gta_attn_fwd(const GtaAttnParams* p, void* stream);

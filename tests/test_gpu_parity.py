@@ -160,6 +160,37 @@ def test_fused_attention_matches_oracle(case, flags):
     assert np.abs(out - ref).max() < _tol(ref, tc)
 
 
+FP32_TOL = 1e-3
+
+
+@pytest.mark.parametrize("case", [
+    (CFG1_B, 2, 2, 16, 16, False, 2, 0.01), (CFG1_A, 2, 2, 1024, 1024, False, 1, 0.01),
+    (MSN_SO3, 5, 5, 256, 256, False, 2, 0.01), (MSN_SO3, 5, 5, 512, 256, True, 1, 1.0),
+    (CLEVR, 2, 2, 300, 300, False, 2, 0.01), (CLEVR, 3, 2, 853, 300, True, 1, 1.0), (MSN_SO3, 1, 5, 1, 256, True, 2, 0.01),
+], ids=["cfg1b", "cfg1a_T2048", "msn_enc", "msn_dec_tc1", "clevr_enc", "clevr_dec_tc1", "render_1q"])
+def test_fp32_inputs_are_fp32_accurate(case):
+    """fp32 q/k/v run the split-precision pipeline (bf16 hi + residual operands, fp32 accumulation): the north-star
+    budget for fp32 is 1e-3 max-abs (relative to max(1, |ref|_max) when trans_coeff = 1 scales the output up)."""
+    base, nq, nk, tq, tk, cross, B, tc = case
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
+    inp = make_inputs(cfg, B, tq, tk, cross=cross, seed=17, dtype=torch.float32)
+    ref = _oracle(cfg, inp, tc)
+    out = _run(cfg, inp, tc)
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() < FP32_TOL * max(1.0, float(np.abs(ref).max()))
+    # peaked attention (large logits): one key dominates each row, so P/V rounding cannot average out
+    inp2 = dict(inp)
+    inp2["q"] = inp["q"] * 6.0
+    ref2 = _oracle(cfg, inp2, tc)
+    out2 = _run(cfg, inp2, tc)
+    assert np.abs(out2 - ref2).max() < FP32_TOL * max(1.0, float(np.abs(ref2).max()))
+    # the opt-out flag multiplies in plain bf16 (bf16 budget)
+    from gta_b200 import _lib
+    out3 = _run(cfg, inp, tc, flags=_lib.GTA_FLAG_FAST_FP32)
+    assert np.abs(out3 - ref).max() < _tol(ref, tc)
+    assert np.abs(out3 - ref).max() > np.abs(out - ref).max()
+
+
 def test_contiguous_and_strided_inputs_agree():
     cfg = GtaConfig(**MSN_SO3, n_q_views=2, n_k_views=2)
     a = make_inputs(cfg, 2, 100, 100, cross=False, seed=3, dtype=torch.bfloat16, packed_layout=True)
