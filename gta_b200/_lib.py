@@ -21,11 +21,12 @@ GTA_FLAG_V0_PIPELINE = 8
 GTA_FLAG_FAST_FP32 = 128
 GTA_FLAG_V1_PIPELINE = 16
 GTA_FLAG_V2_PIPELINE = 32
+GTA_FLAG_V3_PIPELINE = 256
 GTA_FLAG_V4_PIPELINE = 64
 
 
 class GtaReps(ctypes.Structure):
-    _fields_ = [(n, c_void_p) for n in ("se3_q", "se3_k", "so3_q", "so3_k", "so2_q", "so2_k")]
+    _fields_ = [(n, c_void_p) for n in ("se3_q", "se3_k", "so3_q", "so3_k", "so2_q", "so2_k", "se3_qi", "t2_q", "t2_k")]
 
 
 class GtaAttnParams(ctypes.Structure):
@@ -38,6 +39,7 @@ class GtaAttnParams(ctypes.Structure):
         + [("reps", GtaReps), ("trans_coeff", c_void_p), ("scale", c_float)]
         + [(n, c_int) for n in ("in_dtype", "out_dtype", "v_transform")]
         + [("workspace", c_void_p), ("workspace_bytes", c_size_t), ("flags", c_int), ("debug_clocks", c_void_p)]
+        + [("t2", c_int), ("euclid", c_int)]
     )
 
 

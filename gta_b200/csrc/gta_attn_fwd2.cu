@@ -376,7 +376,8 @@ int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st) {
     if ((p.flags & GTA_FLAG_V4_PIPELINE) && p.D <= 96 && ((p.Tq + 127) / 128) % 2 == 0)
         return launch_attn_fwd_v4(p, st);                                                   // S/P decoupled (needs tile pairs)
     if ((p.flags & GTA_FLAG_V2_PIPELINE) && p.D <= 96) return launch_attn_fwd_v2(p, st);    // persistent, epilogue on the softmax warps
-    if (!(p.flags & GTA_FLAG_V1_PIPELINE) && p.D <= 96) return launch_attn_fwd_v3(p, st);  // default: persistent + pre/post warpgroup
+    if ((p.flags & GTA_FLAG_V3_PIPELINE) && p.D <= 96) return launch_attn_fwd_v3(p, st);    // experiment: pre/post warpgroup
+    if (!(p.flags & GTA_FLAG_V1_PIPELINE) && p.D <= 96) return launch_attn_fwd_v5(p, st);  // default: four softmax warpgroups
     const AttnArgs a = make_attn_args(p);
     dim3 grid((p.Tq + 255) / 256, p.H, p.B);
     const bool ib = p.in_dtype == GTA_DTYPE_BF16, ob = p.out_dtype == GTA_DTYPE_BF16;

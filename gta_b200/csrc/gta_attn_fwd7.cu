@@ -1,0 +1,559 @@
+// Fused GTA attention forward, v5 pipeline (default for head dims <= 96): the persistent two-tile pipeline of
+// gta_attn_fwd3.cu with FOUR softmax warpgroups — every 128x128 score tile is split by COLUMNS between two warpgroups
+// (both address the same 128 TMEM lanes; a warp may touch lanes 32*(warp%4)..+31), so the latency of one tile's
+// softmax (TMEM load, max, 128 exponentials per row, pack, TMEM store) is halved and the S -> P -> PV -> QK dependency
+// chain of a query tile shortens from ~3.1 k to ~2 k clocks; with four softmax warps per scheduler the MUFU unit
+// stays busy while one of them waits.  The two halves of a row agree on the running maximum through shared memory
+// (one 256-thread named barrier per key tile, which also orders the in-place P store against the partner's S load),
+// keep partial row sums, and split the epilogue by output columns (each thread drains D/2 accumulator columns with a
+// single TMEM round trip, releases O at once and rotates / stores from registers).
+//
+//   warps 0-3 / 4-7     softmax of query tile A, key columns 0-63 / 64-127    (thread i <-> query row i <-> TMEM lane i)
+//   warps 8-11 / 12-15  softmax of query tile B, key columns 0-63 / 64-127
+//   warp 16             UMMA issuer: PV_X(j) is issued in two halves (keys 0-63 after the first warpgroup's P, keys 64-127
+//                       after the second's)
+//   warp 17             bulk-copy producer for the K'/V' tile images (2-stage ring)
+//   warps 18-19         Q stager, one item ahead (rho_q^{-T} in fp32 registers -> bf16 UMMA operand tiles)
+// Register split (setmaxnreg, 640 threads): softmax warpgroups 104, the fifth warpgroup 96.
+//
+// Reference semantics: source/utils/gta.py:92-279 and source/layers.py:202-211.
+#include <cmath>
+
+#include "attn_common.cuh"
+
+namespace gta {
+
+constexpr int kThreads7 = 640;
+constexpr int kStagerThreads = 64;
+constexpr uint32_t k7TmemSA = 0, k7TmemSB = 128, k7TmemOA = 256, k7TmemOB = 384;
+constexpr float k7RescaleThreshold = 8.0f;   // log2 units
+// Fraction of the exponentials evaluated with poly_exp2x2 instead of MUFU.EX2: pairs with (i % DEN) < NUM.
+#ifndef GTA_V5_REGS_SOFTMAX
+#define GTA_V5_REGS_SOFTMAX 104    // 512 * SOFTMAX + 128 * MISC must equal 65 536
+#define GTA_V5_REGS_MISC 96
+#endif
+__device__ __forceinline__ void named_bar_sync7(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+#ifndef GTA_POLY_NUM
+#define GTA_POLY_NUM 0
+#endif
+#ifndef GTA_POLY_DEN
+#define GTA_POLY_DEN 4
+#endif
+
+template <int D>
+struct Attn7Cfg {
+    static constexpr int kStages = 2;
+    static constexpr uint32_t kTile = 128u * D * 2u;
+    static constexpr uint32_t kQ = 0;                          // [2 buffers][2 tiles]
+    static constexpr uint32_t kK = 4 * kTile;                  // [kStages]
+    static constexpr uint32_t kV = kTile * (4 + kStages);      // [kStages]
+    static constexpr uint32_t kXch = kTile * (4 + 2 * kStages);   // float [2 kinds (max, sum)][X][half][128]
+    static constexpr uint32_t kBars = kXch + 2 * 2 * 2 * 128 * 4;
+    enum : int {
+        bQFull = 0,                        // [buf][X]  count 128 (stager threads)
+        bQFree = 4,                        // [buf][X]  tcgen05.commit after the item's last QK_X
+        bKFull = 8,                        // [kStages]
+        bVFull = bKFull + kStages,
+        bKEmpty = bVFull + kStages,
+        bVEmpty = bKEmpty + kStages,
+        bSFull = bVEmpty + kStages,        // [X] commit
+        bPHalf = bSFull + 2,               // [X] count 128: keys 0..63 of P_X (first softmax warpgroup of the tile)
+        bPFull = bPHalf + 2,               // [X] count 128: keys 64..127 of P_X (second warpgroup)
+        bOFinal = bPFull + 2,              // [X] commit after the item's last PV_X
+        bOFree = bOFinal + 2,              // [X] count 256: O_X drained to registers (both column halves)
+        bCount = bOFree + 2
+    };
+    static constexpr uint32_t kTmemSlot = kBars + bCount * 8;
+    static constexpr uint32_t kUsed = kTmemSlot + 16;
+    static constexpr uint32_t kBytes = (kUsed + 1024 > 120u * 1024u) ? kUsed + 1024 : 120u * 1024u;
+};
+
+struct ItemCoord7 {
+    int b, h, p;
+    bool has_b;
+};
+__device__ __forceinline__ ItemCoord7 decode_item7(int item, int npairs, int H, int Tq) {
+    ItemCoord7 c;
+    c.p = item % npairs;
+    const int bh = item / npairs;
+    c.h = bh % H;
+    c.b = bh / H;
+    c.has_b = (c.p * 256 + 128) < Tq;
+    return c;
+}
+
+template <typename TIn, typename TOut, int D>
+__global__ void __launch_bounds__(kThreads7, 1) attn_fwd7_kernel(const AttnArgs a, const int npairs, const int nitems) {
+    using L = Attn7Cfg<D>;
+    constexpr int NS = L::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = a.ntiles_k;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&bars[L::bQFull + i], kStagerThreads);
+            mbar_init(&bars[L::bQFree + i], 1);
+        }
+        for (int x = 0; x < 2; ++x) {
+            mbar_init(&bars[L::bSFull + x], 1);
+            mbar_init(&bars[L::bPHalf + x], 128);
+            mbar_init(&bars[L::bPFull + x], 128);
+            mbar_init(&bars[L::bOFinal + x], 1);
+            mbar_init(&bars[L::bOFree + x], 256);
+        }
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&bars[L::bKFull + s], 1);
+            mbar_init(&bars[L::bVFull + s], 1);
+            mbar_init(&bars[L::bKEmpty + s], 1);
+            mbar_init(&bars[L::bVEmpty + s], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 16) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const float tc = a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f;
+
+    if (warp < 16) {
+        // =========================================================== softmax warpgroups (+ epilogue)
+        setmaxnreg_inc<GTA_V5_REGS_SOFTMAX>();
+        constexpr int DH = D / 2;            // accumulator columns per thread in the rescale path and the epilogue
+        constexpr int NCH = DH / 8;          // ... as 8-element chunks
+        const int wg = warp >> 2;            // 0..3
+        const int X = wg >> 1;               // query tile
+        const int h = wg & 1;                // key-column half of every score tile / output-column half of O
+        const int r = threadIdx.x & 127;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const uint32_t s_addr = lane_base + (X ? k7TmemSB : k7TmemSA);
+        const uint32_t o_addr = lane_base + (X ? k7TmemOB : k7TmemOA) + h * DH;
+        float* xch_m = reinterpret_cast<float*>(smem + L::kXch) + (X * 2) * 128;          // [half][128] tile maxima
+        float* xch_l = reinterpret_cast<float*>(smem + L::kXch) + (4 + X * 2) * 128;      // [half][128] row sums
+        const float cs = a.scale_log2;
+        const uint64_t cs2 = pack_f32x2(cs, cs);
+        uint32_t gt = 0;      // tiles processed by this warpgroup (s_full phase)
+        uint32_t cnt = 0;     // items processed by this warpgroup (o_final phase)
+        long long* dbg = (a.dbg && threadIdx.x == 0) ? a.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+        long long d_loop = 0, d_epi = 0, d_wait_s = 0, d_wait_o = 0, d_items = 0, d_xch = 0;
+        const long long d_start = dbg ? clock64() : 0;
+
+#pragma unroll 1
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const ItemCoord7 ic = decode_item7(item, npairs, a.H, a.Tq);
+            if (X == 1 && !ic.has_b) continue;
+            float m_used = -INFINITY, l_run = 0.f;      // l_run: partial row sum over this thread's key columns
+            const long long d_t0 = dbg ? clock64() : 0;
+            const int t = ic.p * 256 + X * 128 + r;
+            const bool valid = t < a.Tq;
+            const int tt = valid ? t : a.Tq - 1;
+            const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
+            const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
+
+#pragma unroll 1
+            for (int j = 0; j < n; ++j, ++gt) {
+                if (j == n - 1 && a.v_transform) {
+                    // pull this row's output-rotation operands into L1 one key tile before the epilogue needs them
+                    if (a.hd.se3) prefetch_l1(a.se3_q + view * 16);
+                    if (a.hd.so3) { prefetch_l1(a.so3_q + view * 34); prefetch_l1(a.so3_q + view * 34 + 32); }
+                    if (a.hd.so2)
+                        for (int off = 0; off < a.C * 2; off += 32) prefetch_l1(so2 + off);
+                }
+                const long long d_w0 = dbg ? clock64() : 0;
+                mbar_wait(&bars[L::bSFull + X], gt & 1);
+                if (dbg) d_wait_s += clock64() - d_w0;
+                tc_fence_after();
+                uint32_t sreg[64];
+                tmem_ld32(s_addr + h * 64, sreg);
+                tmem_ld32(s_addr + h * 64 + 32, sreg + 32);
+                tmem_ld_wait();
+                float* s = reinterpret_cast<float*>(sreg);
+                if (j == n - 1) {
+                    const int nvalid = a.Tk - j * 128 - h * 64;      // may be <= 0 for the second half
+                    if (nvalid < 64) {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) if (i >= nvalid) s[i] = -INFINITY;
+                    }
+                }
+                float mx0 = fmax3(s[0], s[1], s[2]), mx1 = fmax3(s[3], s[4], s[5]);
+                float mx2 = fmax3(s[6], s[7], s[8]), mx3 = fmax3(s[9], s[10], s[11]);
+#pragma unroll
+                for (int i = 12; i < 60; i += 8) {
+                    mx0 = fmax3(mx0, s[i], s[i + 1]); mx1 = fmax3(mx1, s[i + 2], s[i + 3]);
+                    mx2 = fmax3(mx2, s[i + 4], s[i + 5]); mx3 = fmax3(mx3, s[i + 6], s[i + 7]);
+                }
+                mx0 = fmax3(mx0, s[60], s[61]); mx1 = fmax3(mx1, s[62], s[63]);
+                const float m_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                // Agree on the tile maximum with the thread that owns the other 64 key columns of this row.  The barrier
+                // also orders this warpgroup's in-place P store (below) after the partner's S load (above): the packed P
+                // of keys 64..127 lands in TMEM columns 32..63, which hold S of keys 32..63.
+                const long long d_x0 = dbg ? clock64() : 0;
+                xch_m[h * 128 + r] = m_half;
+                named_bar_sync7(1 + X, 256);
+                const float m_tile = fmaxf(m_half, xch_m[(h ^ 1) * 128 + r]);
+                if (dbg) d_xch += clock64() - d_x0;
+
+                const bool grow = (m_tile - m_used) * cs > k7RescaleThreshold;   // always true on the item's first tile
+                if (__any_sync(0xffffffffu, grow)) {
+                    const float m_new = grow ? m_tile : m_used;
+                    const float alpha = grow ? fast_exp2((m_used - m_new) * cs) : 1.0f;
+                    l_run *= alpha;
+                    m_used = m_new;
+                    if (j > 0) {
+#pragma unroll 1
+                        for (int c8 = 0; c8 < NCH; ++c8) {        // rare; this thread's half of the accumulator columns
+                            uint32_t o8[8];
+                            tmem_ld8(o_addr + c8 * 8, o8);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o8[i] = __float_as_uint(__uint_as_float(o8[i]) * alpha);
+                            tmem_st8(o_addr + c8 * 8, o8);
+                        }
+                    }
+                }
+
+                const float neg = -m_used * cs;
+                const uint64_t neg2 = pack_f32x2(neg, neg);
+                uint64_t lsum2 = pack_f32x2(0.f, 0.f);
+                // packed in place: P pair i overwrites sreg[i] after s[2i], s[2i+1] were consumed
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const uint64_t x2 = ffma2(pack_f32x2(s[2 * i], s[2 * i + 1]), cs2, neg2);
+                    float p0, p1;
+                    if ((i % GTA_POLY_DEN) < GTA_POLY_NUM) {
+                        poly_exp2x2(x2, p0, p1);
+                    } else {
+                        float x0, x1;
+                        unpack_f32x2(x2, x0, x1);
+                        p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+                    }
+                    lsum2 = fadd2(lsum2, pack_f32x2(p0, p1));
+                    sreg[i] = pack_bf16x2(p0, p1);
+                }
+                tmem_st32(s_addr + h * 32, sreg);
+                float ls0, ls1;
+                unpack_f32x2(lsum2, ls0, ls1);
+                l_run += ls0 + ls1;
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[(h ? L::bPFull : L::bPHalf) + X]);
+            }
+
+            // ---- epilogue of this item: this thread owns output columns [h*D/2, (h+1)*D/2) of its row.
+            const long long d_t1 = dbg ? clock64() : 0;
+            xch_l[h * 128 + r] = l_run;
+            named_bar_sync7(1 + X, 256);
+            const float inv_l = 1.0f / (l_run + xch_l[(h ^ 1) * 128 + r]);
+            mbar_wait(&bars[L::bOFinal + X], cnt & 1);
+            const long long d_t2 = dbg ? clock64() : 0;
+            ++cnt;
+            tc_fence_after();
+            // one TMEM round trip for the whole half row, then O_X is free for the next item's first PV
+            uint32_t oreg[DH];
+            if constexpr (DH >= 32) tmem_ld32(o_addr, oreg);
+            if constexpr (DH % 32 == 16) tmem_ld16(o_addr + (DH / 32) * 32, oreg + (DH / 32) * 32);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[L::bOFree + X]);
+            float* o = reinterpret_cast<float*>(oreg);
+#pragma unroll
+            for (int i = 0; i < DH; ++i) o[i] *= inv_l;
+            if (a.v_transform) {
+                const int e_se3 = a.hd.triv, e_so3 = e_se3 + a.hd.se3, e_so2 = e_so3 + a.hd.so3;
+                const int e0 = h * DH;                       // first element of this thread's columns
+                // one pass per block type, so that only one kind of rep data is live next to the DH accumulator values
+                if (a.hd.se3 && e0 < e_so3 && e0 + DH > e_se3) {
+                    float M[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 q4 = __ldg(reinterpret_cast<const float4*>(a.se3_q + view * 16) + i);
+                        M[4 * i] = q4.x; M[4 * i + 1] = q4.y; M[4 * i + 2] = q4.z; M[4 * i + 3] = q4.w;
+                    }
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int e = e0 + c * 8;
+                        if (e >= e_se3 && e < e_so3) se3_apply(o + c * 8, M, tc);
+                    }
+                }
+                if (a.hd.so3 && e0 < e_so2 && e0 + DH > e_so3) {
+                    float W[34];
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) {
+                        const float2 q2 = __ldg(reinterpret_cast<const float2*>(a.so3_q + view * 34) + i);
+                        W[2 * i] = q2.x; W[2 * i + 1] = q2.y;
+                    }
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int e = e0 + c * 8;
+                        if (e >= e_so3 && e < e_so2) so3_apply<true>(o + c * 8, W);
+                    }
+                }
+                if (a.hd.so2 && e0 + DH > e_so2) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int e = e0 + c * 8;
+                        if (e >= e_so2) {
+                            const So2Chunk sc = load_so2_chunk(so2, e >> 3, a.hd);
+                            const float cs8[8] = {sc.a.x, sc.a.y, sc.a.z, sc.a.w, sc.b.x, sc.b.y, sc.b.z, sc.b.w};
+                            so2_apply<true>(o + c * 8, cs8);
+                        }
+                    }
+                }
+            }
+            if (valid) {
+                TOut* orow = reinterpret_cast<TOut*>(a.out) + ((static_cast<int64_t>(ic.b) * a.Tq + tt) * a.H + ic.h) * D + h * DH;
+                if (sizeof(TOut) == 4) {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c)
+                        st_global_v8(orow + c * 8, make_uint4(oreg[c * 8], oreg[c * 8 + 1], oreg[c * 8 + 2], oreg[c * 8 + 3]),
+                                     make_uint4(oreg[c * 8 + 4], oreg[c * 8 + 5], oreg[c * 8 + 6], oreg[c * 8 + 7]));
+                } else {
+#pragma unroll
+                    for (int c = 0; c + 1 < NCH; c += 2)
+                        st_global_v8(orow + c * 8, pack_chunk_bf16(o + c * 8), pack_chunk_bf16(o + c * 8 + 8));
+                    if (NCH & 1) *reinterpret_cast<uint4*>(orow + (NCH - 1) * 8) = pack_chunk_bf16(o + (NCH - 1) * 8);
+                }
+                if (a.lse && h == 0)
+                    a.lse[(static_cast<int64_t>(ic.b) * a.H + ic.h) * a.Tq + t] = m_used * a.scale - logf(inv_l);
+            }
+            if (dbg) {
+                const long long d_t3 = clock64();
+                d_loop += d_t1 - d_t0; d_wait_o += d_t2 - d_t1; d_epi += d_t3 - d_t2; ++d_items;
+            }
+        }
+        if (dbg) {
+            dbg[0] = clock64() - d_start; dbg[1] = d_loop; dbg[2] = d_epi; dbg[3] = d_wait_s; dbg[4] = d_wait_o;
+            dbg[5] = d_items; dbg[6] = d_xch;
+        }
+    } else {
+      setmaxnreg_dec<GTA_V5_REGS_MISC>();
+      if (warp >= 18) {
+        // =========================================================== Q stager (runs one item ahead)
+        const int r0 = threadIdx.x - 576;    // 0..63; this thread stages rows r0 and r0 + 64 of each tile
+        uint32_t cntx[2] = {0, 0};          // items staged per tile slot (buffer = cnt & 1, phase = (cnt >> 1) & 1)
+#pragma unroll 1
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const ItemCoord7 ic = decode_item7(item, npairs, a.H, a.Tq);
+#pragma unroll 1
+            for (int X = 0; X < 2; ++X) {
+                if (X == 1 && !ic.has_b) continue;
+                const uint32_t c_ = cntx[X]++;
+                const int buf = c_ & 1;
+                if (c_ >= 2) mbar_wait(&bars[L::bQFree + buf * 2 + X], ((c_ >> 1) - 1) & 1);
+                uint8_t* sQ = smem + L::kQ + (buf * 2 + X) * L::kTile;
+#pragma unroll 1
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int r = r0 + rr * 64;
+                    const int t = ic.p * 256 + X * 128 + r;
+                    const bool valid = t < a.Tq;
+                    const int tt = valid ? t : a.Tq - 1;
+                    const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
+                    const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
+                    const TIn* qrow = reinterpret_cast<const TIn*>(a.q) + static_cast<int64_t>(ic.b) * a.q_sb +
+                                      static_cast<int64_t>(ic.h) * a.q_sh + static_cast<int64_t>(tt) * a.q_st;
+                    constexpr int NC = D / 8;
+                    constexpr int G = (sizeof(TIn) == 2) ? NC : ((NC % 6 == 0) ? 6 : 4);   // <= 48 registers of raw data
+                    const float* se3 = a.se3_q + view * 16;
+                    const float* so3 = a.so3_q + view * 34;
+#pragma unroll 1
+                    for (int g = 0; g < NC / G; ++g) {
+                        RawChunk<TIn> raw[G];
+#pragma unroll
+                        for (int i = 0; i < G; ++i) {
+                            zero_raw(raw[i]);
+                            if (valid) load_raw(qrow + (g * G + i) * 8, raw[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < G; ++i) {
+                            float x[8];
+                            raw_to_f32(raw[i], x);
+                            apply_rep_chunk<kModeQ>(x, g * G + i, a.hd, se3, so3, so2, tc);
+                            *reinterpret_cast<uint4*>(sQ + tile_sw64_offset(r, g * G + i)) = pack_chunk_bf16(x);
+                        }
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(&bars[L::bQFull + buf * 2 + X]);
+            }
+        }
+      } else if (warp == 16) {
+            // ======================================================= UMMA issuer
+            constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
+            uint32_t gk = 0;                   // global key-tile counter of this CTA (K/V ring position)
+            uint32_t gtx[2] = {0, 0};          // tiles per softmax warpgroup (p_full phase)
+            uint32_t cntx[2] = {0, 0};         // items per tile slot (Q buffer / o_free phase)
+            const uint32_t bar0 = smem_u32(bars);
+            long long* dbg = (a.dbg && lane == 0) ? a.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
+            long long w_k = 0, w_v = 0, w_p = 0, w_of = 0, w_q = 0;
+#define GTA_TIMED_WAIT(acc, ...)                                 \
+    do {                                                         \
+        const long long t0_ = dbg ? clock64() : 0;               \
+        __VA_ARGS__;                                             \
+        if (dbg) acc += clock64() - t0_;                         \
+    } while (0)
+
+#pragma unroll 1
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const ItemCoord7 ic = decode_item7(item, npairs, a.H, a.Tq);
+                const int nx = ic.has_b ? 2 : 1;
+                uint32_t q_addr[2];
+                for (int X = 0; X < nx; ++X) {
+                    const uint32_t c_ = cntx[X];
+                    const int buf = c_ & 1;
+                    q_addr[X] = smem_u32(smem + L::kQ + (buf * 2 + X) * L::kTile);
+                }
+
+                auto issue_qk = [&](int X, int j) {
+                    const int s = (gk + j) % NS;
+                    if (elect_one()) {
+                        const uint64_t qd = desc_kmajor_sw64(q_addr[X], 0);
+                        const uint64_t kd = desc_kmajor_sw64(smem_u32(smem + L::kK + s * L::kTile), 0);
+                        const uint32_t qlo = static_cast<uint32_t>(qd), qhi = static_cast<uint32_t>(qd >> 32);
+                        const uint32_t klo = static_cast<uint32_t>(kd), khi = static_cast<uint32_t>(kd >> 32);
+                        const uint32_t d_addr = tmem_base + (X ? k7TmemSB : k7TmemSA);
+#pragma unroll
+                        for (int kk = 0; kk < D / 16; ++kk)
+                            umma_ss_lohi(d_addr, qlo + kstep_kmajor_sw64(kk), qhi, klo + kstep_kmajor_sw64(kk), khi, idesc_qk, kk > 0);
+                        if (X == nx - 1) umma_commit_addr(bar0 + (L::bKEmpty + s) * 8);
+                        if (j == n - 1) umma_commit_addr(bar0 + (L::bQFree + (cntx[X] & 1) * 2 + X) * 8);
+                        umma_commit_addr(bar0 + (L::bSFull + X) * 8);
+                    }
+                    __syncwarp();
+                };
+                auto issue_pv = [&](int X, int j) {
+                    const int s = (gk + j) % NS;
+                    const uint32_t par = (gtx[X] + j) & 1;
+                    const uint64_t vd = desc_mnmajor_sw64(smem_u32(smem + L::kV + s * L::kTile), 0);
+                    const uint32_t vlo = static_cast<uint32_t>(vd), vhi = static_cast<uint32_t>(vd >> 32);
+                    const uint32_t d_addr = tmem_base + (X ? k7TmemOB : k7TmemOA);
+                    const uint32_t p_addr = tmem_base + (X ? k7TmemSB : k7TmemSA);
+                    // keys 0..63 (first softmax warpgroup of the tile)
+                    GTA_TIMED_WAIT(w_p, mbar_wait(&bars[L::bPHalf + X], par));
+                    if (j == 0 && cntx[X] > 0) GTA_TIMED_WAIT(w_of, mbar_wait(&bars[L::bOFree + X], (cntx[X] - 1) & 1));
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_ts_lohi(d_addr, p_addr + kk * 8, vlo + kstep_mnmajor_sw64(kk), vhi, idesc_pv,
+                                         (j > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    __syncwarp();
+                    // keys 64..127 (second warpgroup)
+                    GTA_TIMED_WAIT(w_p, mbar_wait(&bars[L::bPFull + X], par));
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 4; kk < 8; ++kk)
+                            umma_ts_lohi(d_addr, p_addr + kk * 8, vlo + kstep_mnmajor_sw64(kk), vhi, idesc_pv, 1u);
+                        if (X == nx - 1) umma_commit_addr(bar0 + (L::bVEmpty + s) * 8);
+                        if (j == n - 1) umma_commit_addr(bar0 + (L::bOFinal + X) * 8);
+                    }
+                    __syncwarp();
+                };
+
+                GTA_TIMED_WAIT(w_k, mbar_wait(&bars[L::bKFull + gk % NS], (gk / NS) & 1));
+                for (int X = 0; X < nx; ++X) {
+                    const uint32_t c_ = cntx[X];
+                    GTA_TIMED_WAIT(w_q, mbar_wait(&bars[L::bQFull + (c_ & 1) * 2 + X], (c_ >> 1) & 1));
+                    tc_fence_after();
+                    issue_qk(X, 0);
+                }
+#pragma unroll 1
+                for (int j = 0; j < n; ++j) {
+                    GTA_TIMED_WAIT(w_v, mbar_wait(&bars[L::bVFull + (gk + j) % NS], ((gk + j) / NS) & 1));
+                    if (j + 1 < n) GTA_TIMED_WAIT(w_k, mbar_wait(&bars[L::bKFull + (gk + j + 1) % NS], ((gk + j + 1) / NS) & 1));
+                    for (int X = 0; X < nx; ++X) {
+                        issue_pv(X, j);
+                        if (j + 1 < n) issue_qk(X, j + 1);
+                    }
+                }
+                gk += n;
+                for (int X = 0; X < nx; ++X) { gtx[X] += n; ++cntx[X]; }
+            }
+            if (dbg) { dbg[8] = w_k; dbg[9] = w_v; dbg[10] = w_p; dbg[11] = w_of; dbg[12] = w_q; }
+#undef GTA_TIMED_WAIT
+      } else if (warp == 17) {
+            // ======================================================= bulk-copy producer
+            uint32_t gk = 0;
+#pragma unroll 1
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const ItemCoord7 ic = decode_item7(item, npairs, a.H, a.Tq);
+                const size_t blob0 = (static_cast<size_t>(ic.b) * a.H + ic.h) * n;
+#pragma unroll 1
+                for (int j = 0; j < n; ++j, ++gk) {
+                    const int s = gk % NS;
+                    if (gk >= NS) mbar_wait(&bars[L::bKEmpty + s], ((gk / NS) - 1) & 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&bars[L::bKFull + s], L::kTile);
+                        bulk_g2s(smem + L::kK + s * L::kTile, a.ws_k + (blob0 + j) * L::kTile, L::kTile, &bars[L::bKFull + s]);
+                    }
+                    if (gk >= NS) mbar_wait(&bars[L::bVEmpty + s], ((gk / NS) - 1) & 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&bars[L::bVFull + s], L::kTile);
+                        bulk_g2s(smem + L::kV + s * L::kTile, a.ws_v + (blob0 + j) * L::kTile, L::kTile, &bars[L::bVFull + s]);
+                    }
+                    __syncwarp();
+                }
+            }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+template <typename TIn, typename TOut, int D>
+static int launch7_one(const AttnArgs& a, const GtaAttnParams& p, cudaStream_t st) {
+    using L = Attn7Cfg<D>;
+    auto kern = attn_fwd7_kernel<TIn, TOut, D>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::kBytes));
+    if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const int npairs = (p.Tq + 255) / 256;
+    const long long nitems = static_cast<long long>(p.B) * p.H * npairs;
+    if (nitems > 0x7fffffffLL) return set_error(GTA_ERR_UNSUPPORTED, "too many work items");
+    const int grid = static_cast<int>(nitems < num_sms ? nitems : num_sms);
+    kern<<<grid, kThreads7, L::kBytes, st>>>(a, npairs, static_cast<int>(nitems));
+    return check_launch("gta_attn_fwd");
+}
+
+template <typename TIn, typename TOut>
+static int launch7_d(const AttnArgs& a, const GtaAttnParams& p, cudaStream_t st) {
+    switch (p.D) {
+        case 32: return launch7_one<TIn, TOut, 32>(a, p, st);
+        case 64: return launch7_one<TIn, TOut, 64>(a, p, st);
+        case 96: return launch7_one<TIn, TOut, 96>(a, p, st);
+    }
+    return set_error(GTA_ERR_UNSUPPORTED, "persistent pipeline supports head dims 32/64/96");
+}
+
+int launch_attn_fwd_v5(const GtaAttnParams& p, cudaStream_t st) {
+    const AttnArgs a = make_attn_args(p);
+    const bool ib = p.in_dtype == GTA_DTYPE_BF16, ob = p.out_dtype == GTA_DTYPE_BF16;
+    if (ib && ob) return launch7_d<__nv_bfloat16, __nv_bfloat16>(a, p, st);
+    if (ib && !ob) return launch7_d<__nv_bfloat16, float>(a, p, st);
+    if (!ib && ob) return launch7_d<float, __nv_bfloat16>(a, p, st);
+    return launch7_d<float, float>(a, p, st);
+}
+
+}  // namespace gta

@@ -32,11 +32,15 @@ class PackedReps:
     so3_k: Optional[torch.Tensor] = None
     so2_q: Optional[torch.Tensor] = None   # [B,Tq,C,2]
     so2_k: Optional[torch.Tensor] = None
+    se3_qi: Optional[torch.Tensor] = None  # [B,Nq,16]  inv(E_q) (euclid_sim only)
+    t2_q: Optional[torch.Tensor] = None    # [B,Tq,2]   patch coordinates of the t2 block
+    t2_k: Optional[torch.Tensor] = None
     n_q_views: int = 1
     n_k_views: int = 1
 
     def c_struct(self) -> GtaReps:
-        return GtaReps(*[_ptr(getattr(self, n)) for n in ("se3_q", "se3_k", "so3_q", "so3_k", "so2_q", "so2_k")])
+        return GtaReps(*[_ptr(getattr(self, n)) for n in ("se3_q", "se3_k", "so3_q", "so3_k", "so2_q", "so2_k",
+                                                           "se3_qi", "t2_q", "t2_k")])
 
 
 def build_reps(extr_q: torch.Tensor, extr_k: torch.Tensor, coord_q: torch.Tensor, coord_k: torch.Tensor, *,

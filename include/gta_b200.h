@@ -49,6 +49,12 @@ typedef struct GtaReps {
     const float* so3_k;
     const float* so2_q;
     const float* so2_k;
+    /* ablation blocks (generic path, see GtaAttnParams.t2 / .euclid) */
+    const float* se3_qi; /* [B,Nq,16] inv(E_q) unscaled (= extras['se3rep_q']); only read when euclid != 0
+                            (source/utils/gta.py:146-156 multiplies the query points by c_q, not by inv_c_q^T) */
+    const float* t2_q;   /* [B,Tq,2] patch coordinates (x,y) of make_T2mats, = extras['t2rep_q'][...,2,:2]
+                            (source/utils/gta.py:72-89) */
+    const float* t2_k;   /* [B,Tk,2] */
 } GtaReps;
 
 typedef struct GtaAttnParams {
@@ -65,7 +71,7 @@ typedef struct GtaAttnParams {
     float* lse; /* optional [B,H,Tq] natural-log-sum-exp of the scaled logits; may be NULL */
     int B, H, Tq, Tk, D;
     int Nq, Nk;                /* views; token t belongs to view t / (T/N)  (gta.py:160-162) */
-    int triv, se3, so3, so2;   /* f_dims, fixed order triv|se3|so3|so2 (gta.py:115) */
+    int triv, se3, so3, so2;   /* f_dims, fixed order triv|se3|so3|so2|t2 (gta.py:115) */
     GtaReps reps;
     const float* trans_coeff;  /* DEVICE pointer to the layer's scalar parameter (layers.py:188-191); NULL => 1.0 */
     float scale;               /* attn_fn.scale / tau  (layers.py:209) */
@@ -75,8 +81,20 @@ typedef struct GtaAttnParams {
     void* workspace;           /* >= gta_attn_fwd_workspace_bytes(...) bytes, 1024-byte aligned */
     size_t workspace_bytes;
     int flags;                 /* GTA_FLAG_* */
-    long long* debug_clocks;   /* optional [num_CTAs,8] clock64 phase stamps of the attention kernel (tools/phase_timing.py); NULL = off */
+    long long* debug_clocks;   /* optional [num_CTAs,16] clock64 phase stamps of the attention kernel (tools/phase_timing*.py); NULL = off */
+    int t2;                    /* f_dims['t2']: 3-vectors transformed by the per-token T(2) matrices (gta.py:221-238,272-274) */
+    int euclid;                /* euclid_sim: se3 block = homogenised 3-vectors (gta.py:146-156,251-253) and the similarity is
+                                  -0.5*|q'-k'|^2 (EuclidAttnFn, source/layers.py:213-224) */
 } GtaAttnParams;
+
+/* Which implementation serves a parameter set:
+ *   fused path   : t2 == 0, euclid == 0 and every block a multiple of 8 elements (all GTA / GTA-so3 configs): rep
+ *                  application fused into the staging pass, the Q stager and the epilogue of the attention kernel.
+ *   generic path : anything else the reference accepts (t2, euclid_sim, blocks that are not multiples of 8 such as
+ *                  runs/clevrtr/GTA/gta_t2 = triv 2 | se3 32 | t2 30): element-wise rep kernels before and after the same
+ *                  tensor-core attention kernel; the euclid similarity is folded into the QK product through two extra
+ *                  key columns holding -0.5*|k'|^2 (hi + residual), head dim padded by 32.  Needs the larger workspace
+ *                  reported by gta_attn_fwd_workspace_bytes_p. */
 
 #define GTA_FLAG_P_IN_TMEM 1   /* (v0 pipeline only) P operand of the PV MMA read from tensor memory */
 #define GTA_FLAG_SKIP_STAGE 2  /* workspace already holds K'/V' of these inputs: launch only the attention kernel */
@@ -85,12 +103,16 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 #define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
 #define GTA_FLAG_V2_PIPELINE 32 /* third generation: persistent CTAs, epilogue and Q staging on the softmax / stager warps */
+#define GTA_FLAG_V3_PIPELINE 256 /* experiment: Q staging + epilogue on a fourth warpgroup, output rows bulk-copied from shared memory */
 #define GTA_FLAG_V4_PIPELINE 64 /* experiment: persistent CTAs, S/P decoupled, one UMMA issuer warp per query tile */
 
 /* Scratch for the rotated K'/V' operand tiles (bf16 inputs, or fp32 inputs with GTA_FLAG_FAST_FP32). */
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D);
 /* Same for any dtype/flags: fp32 inputs use split-precision (hi + residual) tile images, twice the size. */
 size_t gta_attn_fwd_workspace_bytes_ex(int B, int H, int Tk, int D, int in_dtype, int flags);
+
+/* Workspace for exactly this parameter set (covers the generic path; workspace fields of *p are ignored). */
+size_t gta_attn_fwd_workspace_bytes_p(const GtaAttnParams* p);
 
 /* Fused forward: O = rho_q^{-1} softmax((rho_q^{-T} Q)(rho_k K)^T * scale) (rho_k V). */
 int gta_attn_fwd(const GtaAttnParams* p, void* stream);
@@ -104,6 +126,13 @@ int gta_build_reps(const float* extr_q, const float* extr_k, const float* coord_
                    int B, int Nq, int Nk, int Tq, int Tk, int so2_nfreqs, float max_freq_h, float max_freq_w,
                    int shared_freqs, int so3_maxdeg, float* se3_q, float* se3_k, float* so3_q, float* so3_k,
                    float* so2_q, float* so2_k, void* stream);
+
+/* extr [n,4,4] -> inv [n,4,4] (general inverse in fp64, torch.linalg.inv at source/encoder.py:219). */
+int gta_se3_inverse(const float* extr, int64_t n, float* inv, void* stream);
+
+/* make_T2mats (source/utils/gta.py:72-89): coord [n,2] -> mats [n,3,3] = [[1,0,0],[0,1,0],[x,y,1]] and, when
+ * inv_mats != NULL, their inverses [[1,0,0],[0,1,0],[-x,-y,1]] (torch.linalg.inv at source/encoder.py:212). */
+int gta_t2_mats(const float* coord, int64_t n, float* mats, float* inv_mats, void* stream);
 
 /* coord [n,2] -> mats [n, 2*nfreqs, 2, 2] in the reference's layout (freq-major, axis-minor pairs). */
 int gta_so2_mats(const float* coord, int64_t n, int nfreqs, float max_freq_h, float max_freq_w, int shared_freqs,

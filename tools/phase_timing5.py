@@ -1,0 +1,50 @@
+"""Phase clocks of the v5 attention pipeline (gta_attn_fwd7.cu): thread 0 (tile A, first column half) and the UMMA
+issuer lane accumulate clock64 deltas over the CTA's items into GtaAttnParams.debug_clocks [grid][16].
+usage: phase_timing5.py [workload] [B]      (GTA_FLAGS selects another pipeline with the same slots: 32 = v2)"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from bench import WORKLOADS  # noqa: E402
+from gta_b200 import ops  # noqa: E402
+from gta_b200.synth import GtaConfig, make_inputs  # noqa: E402
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "msn_enc"
+    base, nq, nk, tq, tk, cross, B, _ = WORKLOADS[name]
+    if len(sys.argv) > 2:
+        B = int(sys.argv[2])
+    flags = int(os.environ.get("GTA_FLAGS", "0"))
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
+    inp = make_inputs(cfg, B, tq, tk, cross=cross, seed=0, dtype=torch.bfloat16)
+    dev = torch.device("cuda")
+    ek, ck = inp["extr_k"].to(dev), inp["coord_k"].to(dev)
+    eq = inp["extr_q"].to(dev) if cross else ek
+    cq = inp["coord_q"].to(dev) if cross else ck
+    reps = ops.build_reps(eq, ek, cq, ck, so2_nfreqs=cfg.so2, so3_maxdeg=cfg.so3)
+    q, k, v = (inp[n].to(dev) for n in "qkv")
+    tc = torch.tensor([0.01], device=dev)
+    for _ in range(3):
+        ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, flags=flags)
+    dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+    ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, debug_clocks=dbg, flags=flags)
+    torch.cuda.synchronize()
+    d = dbg.cpu().double()
+    d = d[d[:, 5] > 0]
+    items, span = d[:, 5], d[:, 0]
+    ntile = (nk * tk + 127) // 128
+    print(f"{name} B={B} flags={flags} lib={os.environ.get('GTA_B200_LIB', 'default')}: {len(d)} CTAs, items/CTA {items.min():.0f}..{items.max():.0f}")
+    print(f"  CTA span mean {span.mean():9.0f} clk, per item {(span / items).mean():7.0f}   (tensor work per item {ntile * 2 * 2 * 128 * 128 * cfg.head_dim * 2 / 8192:.0f} clk)")
+    for i, nme in ((1, "main loops"), (2, "epilogue (after o_final)"), (4, "o_final wait (+ row-sum exchange)")):
+        print(f"  {nme:34s} per item {(d[:, i] / items).mean():8.0f} clk  ({100 * (d[:, i] / span).mean():5.1f}% of span)")
+    print(f"  per key tile: loop {(d[:, 1] / items / ntile).mean():6.0f} clk, of which s_full wait {(d[:, 3] / items / ntile).mean():6.0f}, max exchange + barrier {(d[:, 6] / items / ntile).mean():6.0f}")
+    for i, nme in ((8, "k_full"), (9, "v_full"), (10, "p_half+p_full"), (11, "o_free"), (12, "q_full")):
+        print(f"  UMMA issuer wait on {nme:14s} per item {(d[:, i] / items).mean():8.0f} clk ({100 * (d[:, i] / span).mean():5.1f}% of span)")
+
+
+if __name__ == "__main__":
+    main()
