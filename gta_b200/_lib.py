@@ -47,11 +47,14 @@ class GtaAttnParams(ctypes.Structure):
 SYMBOLS = {
     "gta_attn_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gta_attn_fwd_workspace_bytes_ex": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "gta_attn_fwd_workspace_bytes_p": (c_size_t, [POINTER(GtaAttnParams)]),
     "gta_attn_fwd": (c_int, [POINTER(GtaAttnParams), c_void_p]),
     "gta_rotate_debug": (c_int, [POINTER(GtaAttnParams), c_void_p, c_void_p, c_void_p, c_void_p]),
     "gta_build_reps": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_float, c_float, c_int, c_int] + [c_void_p] * 7),
     "gta_so2_mats": (c_int, [c_void_p, c_int64, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),
     "gta_wigner_d": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "gta_se3_inverse": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "gta_t2_mats": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gta_umma_probe": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 3),
     "gta_umma_bench": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "gta_softmax_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -20,6 +20,14 @@ int launch_build_reps(const float* extr_q, const float* extr_k, const float* coo
 int launch_so2_mats(const float* coord, int64_t n, int nfreqs, float mfh, float mfw, int shared, float* mats,
                     cudaStream_t st);
 int launch_wigner(const float* R, int64_t n, float* d1, float* d2, cudaStream_t st);
+int launch_se3_inverse(const float* extr, int64_t n, float* inv, cudaStream_t st);
+int launch_t2_mats(const float* coord, int64_t n, float* mats, float* inv, cudaStream_t st);
+
+// Generic path (gta_generic.cu): t2 block, euclid_sim, head layouts with blocks that are not multiples of 8.
+bool attn_needs_generic(const GtaAttnParams& p);
+size_t generic_workspace_bytes(const GtaAttnParams& p);
+int launch_attn_fwd_generic(const GtaAttnParams& p, cudaStream_t st);
+int launch_rotate_debug_generic(const GtaAttnParams& p, float* qt, float* kt, float* vt, cudaStream_t st);
 
 int validate_attn_params(const GtaAttnParams* p);
 int launch_rotate_kv(const GtaAttnParams& p, cudaStream_t st);

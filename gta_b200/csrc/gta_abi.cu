@@ -27,11 +27,16 @@ int validate_attn_params(const GtaAttnParams* p) {
     if (p->B <= 0 || p->H <= 0 || p->Tq <= 0 || p->Tk <= 0) return set_error(GTA_ERR_INVALID, "empty B/H/Tq/Tk");
     if (p->D != 32 && p->D != 64 && p->D != 96 && p->D != 128)
         return set_error(GTA_ERR_UNSUPPORTED, "head dim %d not in {32,64,96,128}", p->D);
-    if (p->triv < 0 || p->se3 < 0 || p->so3 < 0 || p->so2 < 0 || p->triv + p->se3 + p->so3 + p->so2 != p->D)
-        return set_error(GTA_ERR_INVALID, "f_dims (%d,%d,%d,%d) must sum to head dim %d", p->triv, p->se3, p->so3,
-                         p->so2, p->D);
-    if ((p->triv | p->se3 | p->so3 | p->so2) & 7)
-        return set_error(GTA_ERR_UNSUPPORTED, "every f_dims block must be a multiple of 8 elements");
+    if (p->triv < 0 || p->se3 < 0 || p->so3 < 0 || p->so2 < 0 || p->t2 < 0 ||
+        p->triv + p->se3 + p->so3 + p->so2 + p->t2 != p->D)
+        return set_error(GTA_ERR_INVALID, "f_dims (%d,%d,%d,%d,%d) must sum to head dim %d", p->triv, p->se3, p->so3,
+                         p->so2, p->t2, p->D);
+    if (p->se3 % (p->euclid ? 3 : 4) || p->so3 % 8 || p->so2 % 2 || p->t2 % 3)
+        return set_error(GTA_ERR_INVALID, "f_dims: se3 must hold whole %d-vectors, so3 whole [3|5] groups, so2 pairs, t2 triples",
+                         p->euclid ? 3 : 4);
+    if (p->euclid && p->D > 96) return set_error(GTA_ERR_UNSUPPORTED, "euclid_sim needs head dim <= 96");
+    if (p->t2 && (!p->reps.t2_q || !p->reps.t2_k)) return set_error(GTA_ERR_INVALID, "t2 block without t2 coordinates");
+    if (p->euclid && p->se3 && !p->reps.se3_qi) return set_error(GTA_ERR_INVALID, "euclid_sim needs reps.se3_qi = inv(E_q)");
     if (p->Nq <= 0 || p->Nk <= 0 || p->Tq % p->Nq || p->Tk % p->Nk)
         return set_error(GTA_ERR_INVALID, "Tq/Tk must be divisible by the number of views");
     if (p->se3 && (!p->reps.se3_q || !p->reps.se3_k)) return set_error(GTA_ERR_INVALID, "se3 block without se3 reps");
@@ -59,7 +64,7 @@ using namespace gta;
 extern "C" {
 
 const char* gta_last_error(void) { return g_err; }
-int gta_abi_version(void) { return 1; }
+int gta_abi_version(void) { return 2; }
 
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D) {
     if (B <= 0 || H <= 0 || Tk <= 0 || D <= 0) return 0;
@@ -71,14 +76,21 @@ size_t gta_attn_fwd_workspace_bytes_ex(int B, int H, int Tk, int D, int in_dtype
     return (in_dtype == GTA_DTYPE_F32 && !(flags & GTA_FLAG_FAST_FP32)) ? 2 * base : base;
 }
 
+size_t gta_attn_fwd_workspace_bytes_p(const GtaAttnParams* p) {
+    if (!p || p->B <= 0 || p->H <= 0 || p->Tq <= 0 || p->Tk <= 0 || p->D <= 0) return 0;
+    if (attn_needs_generic(*p)) return generic_workspace_bytes(*p);
+    return gta_attn_fwd_workspace_bytes_ex(p->B, p->H, p->Tk, p->D, p->in_dtype, p->flags);
+}
+
 int gta_attn_fwd(const GtaAttnParams* p, void* stream) {
     int rc = validate_attn_params(p);
     if (rc) return rc;
-    const size_t need = gta_attn_fwd_workspace_bytes_ex(p->B, p->H, p->Tk, p->D, p->in_dtype, p->flags);
+    const size_t need = gta_attn_fwd_workspace_bytes_p(p);
     if (!p->workspace || p->workspace_bytes < need)
         return set_error(GTA_ERR_INVALID, "workspace too small (need %zu bytes)", need);
     if (reinterpret_cast<uintptr_t>(p->workspace) & 1023) return set_error(GTA_ERR_INVALID, "workspace must be 1024-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (attn_needs_generic(*p)) return launch_attn_fwd_generic(*p, st);
     if (!(p->flags & GTA_FLAG_SKIP_STAGE)) {
         rc = launch_rotate_kv(*p, st);
         if (rc) return rc;
@@ -91,6 +103,7 @@ int gta_attn_fwd(const GtaAttnParams* p, void* stream) {
 int gta_rotate_debug(const GtaAttnParams* p, float* qt, float* kt, float* vt, void* stream) {
     int rc = validate_attn_params(p);
     if (rc) return rc;
+    if (attn_needs_generic(*p)) return launch_rotate_debug_generic(*p, qt, kt, vt, static_cast<cudaStream_t>(stream));
     return launch_rotate_debug(*p, qt, kt, vt, static_cast<cudaStream_t>(stream));
 }
 
@@ -106,6 +119,14 @@ int gta_build_reps(const float* extr_q, const float* extr_k, const float* coord_
 int gta_so2_mats(const float* coord, int64_t n, int nfreqs, float max_freq_h, float max_freq_w, int shared_freqs,
                  float* mats, void* stream) {
     return launch_so2_mats(coord, n, nfreqs, max_freq_h, max_freq_w, shared_freqs, mats, static_cast<cudaStream_t>(stream));
+}
+
+int gta_se3_inverse(const float* extr, int64_t n, float* inv, void* stream) {
+    return launch_se3_inverse(extr, n, inv, static_cast<cudaStream_t>(stream));
+}
+
+int gta_t2_mats(const float* coord, int64_t n, float* mats, float* inv_mats, void* stream) {
+    return launch_t2_mats(coord, n, mats, inv_mats, static_cast<cudaStream_t>(stream));
 }
 
 int gta_wigner_d(const float* R, int64_t n, float* d1, float* d2, void* stream) {

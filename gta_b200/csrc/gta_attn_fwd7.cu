@@ -14,7 +14,7 @@
 //                       after the second's)
 //   warp 17             bulk-copy producer for the K'/V' tile images (2-stage ring)
 //   warps 18-19         Q stager, one item ahead (rho_q^{-T} in fp32 registers -> bf16 UMMA operand tiles)
-// Register split (setmaxnreg, 640 threads): softmax warpgroups 104, the fifth warpgroup 96.
+// Registers: 640 threads x 96 (no setmaxnreg reallocation, see GTA_V5_REGS_*).
 //
 // Reference semantics: source/utils/gta.py:92-279 and source/layers.py:202-211.
 #include <cmath>
@@ -29,7 +29,10 @@ constexpr uint32_t k7TmemSA = 0, k7TmemSB = 128, k7TmemOA = 256, k7TmemOB = 384;
 constexpr float k7RescaleThreshold = 8.0f;   // log2 units
 // Fraction of the exponentials evaluated with poly_exp2x2 instead of MUFU.EX2: pairs with (i % DEN) < NUM.
 #ifndef GTA_V5_REGS_SOFTMAX
-#define GTA_V5_REGS_SOFTMAX 104    // 512 * SOFTMAX + 128 * MISC must equal 65 536
+// 640 threads launch with 96 registers each (61 440 of the SM's 65 536: the launch granularity leaves the rest unused, and
+// setmaxnreg can only move registers that another warpgroup of the CTA released, so 512*SOFTMAX + 128*MISC <= 61 440).
+// 96/96 = no reallocation: the softmax loop holds 64 scores + ~25 other values and does not spill at 96.
+#define GTA_V5_REGS_SOFTMAX 96
 #define GTA_V5_REGS_MISC 96
 #endif
 __device__ __forceinline__ void named_bar_sync7(int id, int nthreads) {
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(kThreads7, 1) attn_fwd7_kernel(const AttnArgs 
 
     if (warp < 16) {
         // =========================================================== softmax warpgroups (+ epilogue)
-        setmaxnreg_inc<GTA_V5_REGS_SOFTMAX>();
+        if constexpr (GTA_V5_REGS_SOFTMAX != 96) setmaxnreg_inc<GTA_V5_REGS_SOFTMAX>();
         constexpr int DH = D / 2;            // accumulator columns per thread in the rescale path and the epilogue
         constexpr int NCH = DH / 8;          // ... as 8-element chunks
         const int wg = warp >> 2;            // 0..3
@@ -336,7 +339,7 @@ __global__ void __launch_bounds__(kThreads7, 1) attn_fwd7_kernel(const AttnArgs 
             dbg[5] = d_items; dbg[6] = d_xch;
         }
     } else {
-      setmaxnreg_dec<GTA_V5_REGS_MISC>();
+      if constexpr (GTA_V5_REGS_MISC != 96) setmaxnreg_dec<GTA_V5_REGS_MISC>();
       if (warp >= 18) {
         // =========================================================== Q stager (runs one item ahead)
         const int r0 = threadIdx.x - 576;    // 0..63; this thread stages rows r0 and r0 + 64 of each tile

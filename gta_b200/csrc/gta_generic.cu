@@ -1,0 +1,298 @@
+// Generic rep application for the configurations the fused kernels do not cover: the T(2) block (`t2`), the euclid
+// similarity (`euclid_sim`) and head layouts whose blocks are not multiples of 8 elements (e.g. runs/clevrtr/GTA/gta_t2:
+// triv 2 | se3 32 | t2 30).  One thread per OUTPUT ELEMENT evaluates its row of the block-diagonal rep
+//   q' = rho_q^{-T} q,  k' = rho_k k,  v' = rho_k v   (source/utils/gta.py:127-242)
+// into dense, padded operand tensors; the tensor-core attention kernel then runs on them with an all-trivial head
+// layout, and a second element-wise pass applies rho_q^{-1} to its fp32 output (gta.py:246-276).
+//
+// euclid_sim (EuclidAttnFn, source/layers.py:213-224): sim = q'.k' - |q'|^2/2 - |k'|^2/2.  The -|q'|^2/2 term is constant
+// along the softmax axis and cancels; -|k'|^2/2 is folded into the QK product through two extra operand columns
+// (k'[D] = hi, k'[D+1] = residual of -|k'|^2/2, q'[D] = q'[D+1] = 1), the head dim being padded by 32.
+#include "common.cuh"
+#include "reps.cuh"
+
+namespace gta {
+
+struct GenDims {
+    int triv, se3, so3, so2, t2, euclid;
+};
+
+struct GenArgs {
+    const void* x;             // modes Q/KV: [B,H,T,D] strided; mode Out: fp32 [B,T,H,Da] contiguous
+    int64_t sb, sh, st;
+    void* out;                 // modes Q/KV: [B,H,T,Da] contiguous (TStore); mode Out: [B,T,H,D] (TStore)
+    int B, H, T, D, Da, N, tpv, C;
+    GenDims gd;
+    const float* se3m;         // [B,N,16]: Q: E_q (euclid: inv E_q); KV: inv E_k; Out: E_q
+    const float* so3m;         // [B,N,34]
+    const float* so2cs;        // [B,T,C,2]
+    const float* xy;           // [B,T,2]
+    const float* tc_ptr;
+    int mode;                  // RepMode
+    int rotate;                // 0: copy (v_transform = False)
+    int ones;                  // euclid, query side: columns D, D+1 = 1
+};
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// One output element e of the rep applied to a head row; ld(i) reads input element i of the same row.
+template <typename Ld>
+__device__ float gen_element(const GenArgs& a, int e, size_t view, size_t tok, float tc, Ld ld) {
+    const GenDims& g = a.gd;
+    const int mode = a.mode;
+    if (e < g.triv) return ld(e);
+    int e1 = e - g.triv;
+    if (e1 < g.se3) {
+        const float* M = a.se3m + view * 16;
+        if (!g.euclid) {                       // 4-vectors, (M * scale_mask(tc)) or its transpose (gta.py:160-167,255-257)
+            const int base = e - (e1 & 3), i = e1 & 3;
+            const float x0 = ld(base), x1 = ld(base + 1), x2 = ld(base + 2), x3 = ld(base + 3);
+            if (mode == kModeQ) {
+                if (i < 3) return fmaf(M[i], x0, fmaf(M[4 + i], x1, M[8 + i] * x2));
+                return fmaf(tc, fmaf(M[3], x0, fmaf(M[7], x1, M[11] * x2)), M[15] * x3);
+            }
+            if (i < 3) return fmaf(M[4 * i], x0, fmaf(M[4 * i + 1], x1, fmaf(M[4 * i + 2], x2, M[4 * i + 3] * tc * x3)));
+            return M[15] * x3;
+        }
+        // euclid: homogenised 3-vectors, no transpose on the query side (gta.py:146-156,251-253)
+        const int i = e1 % 3, base = e - i;
+        const float x0 = ld(base), x1 = ld(base + 1), x2 = ld(base + 2);
+        return fmaf(M[4 * i], x0, fmaf(M[4 * i + 1], x1, fmaf(M[4 * i + 2], x2, M[4 * i + 3] * tc)));
+    }
+    int e2 = e1 - g.se3;
+    if (e2 < g.so3) {                          // [3 | 5] groups, Wigner D_1 / D_2 (gta.py:182-201,259-268)
+        const float* W = a.so3m + view * 34;
+        const int i = e2 & 7, base = e - i;
+        const bool tr = mode == kModeOut;
+        float s = 0.f;
+        if (i < 3) {
+            for (int j = 0; j < 3; ++j) s = fmaf(tr ? W[j * 3 + i] : W[i * 3 + j], ld(base + j), s);
+        } else {
+            const int ii = i - 3;
+            for (int j = 0; j < 5; ++j) s = fmaf(tr ? W[9 + j * 5 + ii] : W[9 + ii * 5 + j], ld(base + 3 + j), s);
+        }
+        return s;
+    }
+    int e3 = e2 - g.so3;
+    if (e3 < g.so2) {                          // pairs rotated by the token's angles (gta.py:203-219,269-271)
+        const int pr = e3 >> 1, i = e3 & 1, base = e - i;
+        const float* cs = a.so2cs + (tok * a.C + pr) * 2;
+        const float c = cs[0], s = mode == kModeOut ? -cs[1] : cs[1];
+        const float x0 = ld(base), x1 = ld(base + 1);
+        return i == 0 ? fmaf(c, x0, -s * x1) : fmaf(s, x0, c * x1);
+    }
+    {                                          // t2: 3-vectors, T = [[1,0,0],[0,1,0],[x,y,1]] (gta.py:72-89,221-238,272-274)
+        const int e4 = e3 - g.so2, i = e4 % 3, base = e - i;
+        const float px = a.xy[tok * 2], py = a.xy[tok * 2 + 1];
+        const float x0 = ld(base), x1 = ld(base + 1), x2 = ld(base + 2);
+        if (mode == kModeQ) return i == 0 ? fmaf(-px, x2, x0) : (i == 1 ? fmaf(-py, x2, x1) : x2);   // (T^-1)^T
+        if (mode == kModeKV) return i == 2 ? fmaf(px, x0, fmaf(py, x1, x2)) : (i == 0 ? x0 : x1);    // T
+        return i == 2 ? fmaf(-px, x0, fmaf(-py, x1, x2)) : (i == 0 ? x0 : x1);                      // T^-1
+    }
+}
+
+// modes Q / KV: strided [B,H,T,D] input (TIn) -> dense [B,H,T,Da] (TStore); columns >= D: 0 (or 1, see `ones`).
+template <typename TIn, typename TStore>
+__global__ void gen_rotate_in_kernel(const GenArgs a) {
+    const int64_t total = static_cast<int64_t>(a.B) * a.H * a.T * a.Da;
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int e = static_cast<int>(i % a.Da);
+    int64_t r = i / a.Da;
+    const int t = static_cast<int>(r % a.T); r /= a.T;
+    const int h = static_cast<int>(r % a.H);
+    const int b = static_cast<int>(r / a.H);
+    float y;
+    if (e >= a.D) {
+        y = (a.ones && e < a.D + 2) ? 1.0f : 0.0f;
+    } else {
+        const TIn* row = reinterpret_cast<const TIn*>(a.x) + b * a.sb + h * a.sh + t * a.st;
+        auto ld = [&](int idx) { return to_f32<TIn>(row[idx]); };
+        if (!a.rotate) y = ld(e);
+        else y = gen_element(a, e, static_cast<size_t>(b) * a.N + t / a.tpv, static_cast<size_t>(b) * a.T + t,
+                             a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f, ld);
+    }
+    reinterpret_cast<TStore*>(a.out)[i] = from_f32<TStore>(y);
+}
+
+// euclid: k'[D], k'[D+1] = -|k'|^2/2 as value + residual in the storage type (one thread per key row, on the
+// STORED — already rounded — operand values so that the folded similarity is self-consistent).
+template <typename TStore>
+__global__ void gen_key_bias_kernel(TStore* __restrict__ kt, int64_t rows, int D, int Da) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    TStore* row = kt + i * Da;
+    float s = 0.f;
+    for (int e = 0; e < D; ++e) { const float v = to_f32<TStore>(row[e]); s = fmaf(v, v, s); }
+    s *= -0.5f;
+    const TStore hi = from_f32<TStore>(s);
+    row[D] = hi;
+    row[D + 1] = from_f32<TStore>(s - to_f32<TStore>(hi));
+}
+
+// mode Out: fp32 [B,T,H,Da] -> [B,T,H,D] (TOut) with rho_q^{-1} applied.
+template <typename TOut>
+__global__ void gen_rotate_out_kernel(const GenArgs a) {
+    const int64_t total = static_cast<int64_t>(a.B) * a.T * a.H * a.D;
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int e = static_cast<int>(i % a.D);
+    int64_t r = i / a.D;
+    const int h = static_cast<int>(r % a.H); r /= a.H;
+    const int t = static_cast<int>(r % a.T);
+    const int b = static_cast<int>(r / a.T);
+    const float* row = reinterpret_cast<const float*>(a.x) + ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.Da;
+    auto ld = [&](int idx) { return row[idx]; };
+    float y;
+    if (!a.rotate) y = ld(e);
+    else y = gen_element(a, e, static_cast<size_t>(b) * a.N + t / a.tpv, static_cast<size_t>(b) * a.T + t,
+                         a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f, ld);
+    reinterpret_cast<TOut*>(a.out)[i] = from_f32<TOut>(y);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+bool attn_needs_generic(const GtaAttnParams& p) {
+    return p.t2 > 0 || p.euclid || ((p.triv | p.se3 | p.so3 | p.so2) & 7);
+}
+static int padded_dim(const GtaAttnParams& p) { return p.euclid ? p.D + 32 : p.D; }
+static size_t align_up(size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); }
+static size_t elt(int dtype) { return dtype == GTA_DTYPE_BF16 ? 2 : 4; }
+
+// The core kernel's flags on the generic path: staging flags make no sense here (the operands are rebuilt every call);
+// the split-precision pipeline exists for head dims <= 96 only, a padded head dim of 128 multiplies in bf16.
+static int core_flags(const GtaAttnParams& p) {
+    int f = p.flags & ~(GTA_FLAG_SKIP_STAGE | GTA_FLAG_STAGE_ONLY);
+    if (p.in_dtype == GTA_DTYPE_F32 && padded_dim(p) > 96) f |= GTA_FLAG_FAST_FP32;
+    return f;
+}
+
+struct GenLayout {
+    size_t q, k, v, o, core, total;
+};
+static GenLayout gen_layout(const GtaAttnParams& p) {
+    const int Da = padded_dim(p);
+    const size_t es = elt(p.in_dtype);
+    GenLayout l;
+    l.q = 0;
+    l.k = l.q + align_up(static_cast<size_t>(p.B) * p.H * p.Tq * Da * es);
+    l.v = l.k + align_up(static_cast<size_t>(p.B) * p.H * p.Tk * Da * es);
+    l.o = l.v + align_up(static_cast<size_t>(p.B) * p.H * p.Tk * Da * es);
+    l.core = l.o + align_up(static_cast<size_t>(p.B) * p.H * p.Tq * Da * 4);
+    l.total = l.core + gta_attn_fwd_workspace_bytes_ex(p.B, p.H, p.Tk, Da, p.in_dtype, core_flags(p));
+    return l;
+}
+size_t generic_workspace_bytes(const GtaAttnParams& p) { return gen_layout(p).total; }
+
+static GenArgs make_gen_args(const GtaAttnParams& p, int which /*0 q, 1 k, 2 v, 3 out*/) {
+    GenArgs a;
+    const bool qside = which == 0 || which == 3;
+    a.x = which == 0 ? p.q : (which == 1 ? p.k : p.v);
+    a.sb = which == 0 ? p.q_stride_b : (which == 1 ? p.k_stride_b : p.v_stride_b);
+    a.sh = which == 0 ? p.q_stride_h : (which == 1 ? p.k_stride_h : p.v_stride_h);
+    a.st = which == 0 ? p.q_stride_t : (which == 1 ? p.k_stride_t : p.v_stride_t);
+    a.out = nullptr;
+    a.B = p.B; a.H = p.H; a.D = p.D; a.Da = padded_dim(p);
+    a.T = qside ? p.Tq : p.Tk; a.N = qside ? p.Nq : p.Nk; a.tpv = a.T / a.N;
+    a.C = p.so2 >> 1;
+    a.gd = GenDims{p.triv, p.se3, p.so3, p.so2, p.t2, p.euclid};
+    a.mode = which == 0 ? kModeQ : (which == 3 ? kModeOut : kModeKV);
+    a.se3m = which == 0 ? (p.euclid ? p.reps.se3_qi : p.reps.se3_q) : (which == 3 ? p.reps.se3_q : p.reps.se3_k);
+    a.so3m = qside ? p.reps.so3_q : p.reps.so3_k;
+    a.so2cs = qside ? p.reps.so2_q : p.reps.so2_k;
+    a.xy = qside ? p.reps.t2_q : p.reps.t2_k;
+    a.tc_ptr = p.trans_coeff;
+    a.rotate = (which < 2) || p.v_transform;
+    a.ones = (which == 0 && p.euclid) ? 1 : 0;
+    return a;
+}
+
+template <typename TIn, typename TStore>
+static void launch_in(const GenArgs& a, cudaStream_t st) {
+    const int64_t total = static_cast<int64_t>(a.B) * a.H * a.T * a.Da;
+    gen_rotate_in_kernel<TIn, TStore><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(a);
+}
+
+int launch_attn_fwd_generic(const GtaAttnParams& p, cudaStream_t st) {
+    const int Da = padded_dim(p);
+    if (Da > 128) return set_error(GTA_ERR_UNSUPPORTED, "euclid_sim needs head dim + 32 <= 128");
+    if (p.euclid && p.lse) return set_error(GTA_ERR_UNSUPPORTED, "lse output is not defined for euclid_sim");
+    const GenLayout l = gen_layout(p);
+    uint8_t* ws = static_cast<uint8_t*>(p.workspace);
+    const bool bf = p.in_dtype == GTA_DTYPE_BF16;
+    for (int which = 0; which < 3; ++which) {
+        GenArgs a = make_gen_args(p, which);
+        a.out = ws + (which == 0 ? l.q : (which == 1 ? l.k : l.v));
+        if (bf) launch_in<__nv_bfloat16, __nv_bfloat16>(a, st); else launch_in<float, float>(a, st);
+    }
+    if (p.euclid) {
+        const int64_t rows = static_cast<int64_t>(p.B) * p.H * p.Tk;
+        const unsigned blocks = static_cast<unsigned>((rows + 127) / 128);
+        if (bf) gen_key_bias_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(ws + l.k), rows, p.D, Da);
+        else gen_key_bias_kernel<float><<<blocks, 128, 0, st>>>(reinterpret_cast<float*>(ws + l.k), rows, p.D, Da);
+    }
+    int rc = check_launch("gta_attn_fwd (generic rep application)");
+    if (rc) return rc;
+
+    GtaAttnParams c = p;                       // the tensor-core attention on the prepared operands
+    c.q = ws + l.q; c.k = ws + l.k; c.v = ws + l.v;
+    c.q_stride_t = c.k_stride_t = c.v_stride_t = Da;
+    c.q_stride_h = static_cast<int64_t>(p.Tq) * Da; c.k_stride_h = c.v_stride_h = static_cast<int64_t>(p.Tk) * Da;
+    c.q_stride_b = c.q_stride_h * p.H; c.k_stride_b = c.v_stride_b = c.k_stride_h * p.H;
+    c.out = ws + l.o; c.out_dtype = GTA_DTYPE_F32;
+    c.D = Da; c.triv = Da; c.se3 = c.so3 = c.so2 = c.t2 = 0; c.euclid = 0;
+    c.reps = GtaReps{};
+    c.trans_coeff = nullptr;
+    c.v_transform = 0;
+    c.flags = core_flags(p);
+    c.workspace = ws + l.core;
+    c.workspace_bytes = p.workspace_bytes - l.core;
+    rc = gta_attn_fwd(&c, st);
+    if (rc) return rc;
+
+    GenArgs o = make_gen_args(p, 3);
+    o.x = ws + l.o;
+    o.out = p.out;
+    const int64_t total = static_cast<int64_t>(p.B) * p.Tq * p.H * p.D;
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    if (p.out_dtype == GTA_DTYPE_BF16) gen_rotate_out_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(o);
+    else gen_rotate_out_kernel<float><<<blocks, 256, 0, st>>>(o);
+    return check_launch("gta_attn_fwd (generic output rep)");
+}
+
+// fp32 rotated operands [B,H,T,D] (no padding) for tests.
+int launch_rotate_debug_generic(const GtaAttnParams& p, float* qt, float* kt, float* vt, cudaStream_t st) {
+    for (int which = 0; which < 3; ++which) {
+        float* out = which == 0 ? qt : (which == 1 ? kt : vt);
+        if (!out) continue;
+        GenArgs a = make_gen_args(p, which);
+        a.Da = p.D; a.ones = 0;
+        a.out = out;
+        if (p.in_dtype == GTA_DTYPE_BF16) launch_in<__nv_bfloat16, float>(a, st); else launch_in<float, float>(a, st);
+    }
+    return check_launch("gta_rotate_debug (generic)");
+}
+
+__global__ void t2_mats_kernel(const float* __restrict__ coord, int64_t n, float* __restrict__ mats, float* __restrict__ inv) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = coord[i * 2], y = coord[i * 2 + 1];
+    const float m[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, x, y, 1.f};
+    for (int j = 0; j < 9; ++j) mats[i * 9 + j] = m[j];
+    if (inv) {
+        const float v[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, -x, -y, 1.f};
+        for (int j = 0; j < 9; ++j) inv[i * 9 + j] = v[j];
+    }
+}
+
+int launch_t2_mats(const float* coord, int64_t n, float* mats, float* inv, cudaStream_t st) {
+    if (n <= 0 || !coord || !mats) return set_error(GTA_ERR_INVALID, "gta_t2_mats: empty input");
+    t2_mats_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(coord, n, mats, inv);
+    return check_launch("gta_t2_mats");
+}
+
+}  // namespace gta

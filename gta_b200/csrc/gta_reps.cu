@@ -121,6 +121,16 @@ __global__ void so2_table_kernel(const float* __restrict__ coord, int64_t ntok, 
     if (mats) { mats[i * 4] = c; mats[i * 4 + 1] = -s; mats[i * 4 + 2] = s; mats[i * 4 + 3] = c; }
 }
 
+// torch.linalg.inv of a batch of 4x4 extrinsics (source/encoder.py:219).
+__global__ void se3_inverse_kernel(const float* __restrict__ E, int64_t n, float* __restrict__ out) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double e[16], ie[16];
+    for (int j = 0; j < 16; ++j) e[j] = static_cast<double>(E[i * 16 + j]);
+    if (!inv4(e, ie)) for (int j = 0; j < 16; ++j) ie[j] = nan("");
+    for (int j = 0; j < 16; ++j) out[i * 16 + j] = static_cast<float>(ie[j]);
+}
+
 __global__ void wigner_kernel(const float* __restrict__ R, int64_t n, float* __restrict__ d1, float* __restrict__ d2) {
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -170,6 +180,12 @@ int launch_so2_mats(const float* coord, int64_t n, int nfreqs, float mfh, float 
     so2_table_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, st>>>(coord, n, nfreqs, two_pi_times(mfh),
                                                                                two_pi_times(mfw), shared, nullptr, mats);
     return check_launch("gta_so2_mats");
+}
+
+int launch_se3_inverse(const float* extr, int64_t n, float* inv, cudaStream_t st) {
+    if (n <= 0 || !extr || !inv) return set_error(GTA_ERR_INVALID, "gta_se3_inverse: empty input");
+    se3_inverse_kernel<<<static_cast<unsigned>((n + 63) / 64), 64, 0, st>>>(extr, n, inv);
+    return check_launch("gta_se3_inverse");
 }
 
 int launch_wigner(const float* R, int64_t n, float* d1, float* d2, cudaStream_t st) {

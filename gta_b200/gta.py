@@ -6,9 +6,10 @@ Same names, argument meaning and return convention as the reference so that it d
     import gta_b200.gta as fast
     fast.install()        # rebinds source.layers.multihead_geometric_transform_attention (+ source.utils.gta)
 
-Forward only (inference / no_grad).  Calls that need autograd, the attention map, the `t2` block or the
-euclid similarity are delegated to the original reference function when it was captured by install(), and raise
-NotImplementedError otherwise — there is no silent CPU or PyTorch fallback inside this package.
+Forward only (inference / no_grad).  Every f_dims layout and flag of the reference function is served by the CUDA
+library (the `t2` block, `euclid_sim` and layouts with blocks that are not multiples of 8 through its generic path).
+Calls that need autograd or a CPU tensor are delegated to the original reference function when it was captured by
+install(), and raise NotImplementedError otherwise — there is no silent CPU or PyTorch fallback inside this package.
 """
 from __future__ import annotations
 
@@ -43,11 +44,17 @@ def make_SO2mats(coord, nfreqs, max_freqs=(1, 1), shared_freqs=False):
     return m.reshape(*coord.shape[:-1], nfreqs, 2, 2, 2)
 
 
-def _pack_reps(reps: dict, f_dims: dict, B: int) -> PackedReps:
+def make_T2mats(coord):
+    """coord [..., 2] -> [..., 3, 3] exactly as source/utils/gta.py:72-89 returns it."""
+    return ops.t2_mats(coord)
+
+
+def _pack_reps(reps: dict, f_dims: dict, B: int, euclid: bool = False) -> PackedReps:
     """Reference-format rep tensors (the `extras` dict) -> packed fp32 tables.  Cached in the dict, keyed on the
     identity of the source tensors (the decoder overwrites the *_q entries, decoder.py:259-346)."""
     g = lambda n: int(f_dims.get(n, 0) or 0)
-    src = tuple(id(reps.get(n)) for n in ("inv_se3rep_q", "se3rep_k", "so3rep_q", "so3rep_k", "so2rep_q", "so2rep_k"))
+    src = tuple(id(reps.get(n)) for n in ("inv_se3rep_q", "se3rep_k", "so3rep_q", "so3rep_k", "so2rep_q", "so2rep_k",
+                                          "se3rep_q", "t2rep_q", "t2rep_k")) + (bool(euclid),)
     hit = reps.get(_PACK_KEY)
     if hit is not None and hit[0] == src:
         return hit[1]
@@ -57,6 +64,13 @@ def _pack_reps(reps: dict, f_dims: dict, B: int) -> PackedReps:
         p.se3_q = f(reps["inv_se3rep_q"]).reshape(B, -1, 16).contiguous()
         p.se3_k = f(reps["se3rep_k"]).reshape(B, -1, 16).contiguous()
         p.n_q_views, p.n_k_views = p.se3_q.shape[1], p.se3_k.shape[1]
+        if euclid:
+            p.se3_qi = f(reps["se3rep_q"]).reshape(B, -1, 16).contiguous()
+    if g("t2"):
+        # make_T2mats puts the token's coordinates in the last row of an otherwise constant matrix (gta.py:85-89)
+        xy = lambda m: f(m)[..., 2, :2].reshape(B, -1, 2).contiguous()
+        p.t2_q = xy(reps["t2rep_q"])
+        p.t2_k = p.t2_q if reps["t2rep_k"] is reps["t2rep_q"] else xy(reps["t2rep_k"])
     if g("so3"):
         dq, dk = reps["so3rep_q"], reps["so3rep_k"]
         if len(dq) != 2 or dq[0].shape[-1] != 3 or dq[1].shape[-1] != 5:
@@ -88,10 +102,6 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
     args = (q, k, v, attn_fn, f_dims, reps)
     kw = dict(trans_coeff=trans_coeff, v_transform=v_transform, euclid=euclid, **kwargs)
     g = lambda n: int(f_dims.get(n, 0) or 0)
-    if euclid:
-        return _delegate("euclid similarity", *args, **kw)
-    if g("t2"):
-        return _delegate("the t2 block", *args, **kw)
     if not q.is_cuda:
         return _delegate("a non-CUDA tensor", *args, **kw)
     if q.dtype not in (torch.bfloat16, torch.float32) or k.dtype != q.dtype or v.dtype != q.dtype:
@@ -99,7 +109,7 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
     if torch.is_grad_enabled() and any(t.requires_grad for t in (q, k, v)):
         return _delegate("autograd (the fused backward is not implemented yet)", *args, **kw)
     B, H, Tq, D = q.shape
-    packed = _pack_reps(reps, f_dims, B)
+    packed = _pack_reps(reps, f_dims, B, euclid)
     if g("so3") and not g("se3"):
         return _delegate("so3 without se3 (undefined in the reference as well, SURVEY T5)", *args, **kw)
     if not g("se3") and not g("so3"):
@@ -111,7 +121,8 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
     tc = None
     if g("se3"):
         tc = trans_coeff if torch.is_tensor(trans_coeff) else torch.tensor([float(trans_coeff)], device=q.device)
-    out = ops.gta_attention_fwd(q, k, v, packed, f_dims, trans_coeff=tc, scale=scale, v_transform=v_transform)
+    out = ops.gta_attention_fwd(q, k, v, packed, f_dims, trans_coeff=tc, scale=scale, v_transform=v_transform,
+                                euclid=euclid)
     return out, None
 
 

@@ -45,7 +45,7 @@ class PackedReps:
 
 def build_reps(extr_q: torch.Tensor, extr_k: torch.Tensor, coord_q: torch.Tensor, coord_k: torch.Tensor, *,
                so2_nfreqs: int, so3_maxdeg: int, max_freq_h: float = 1.0, max_freq_w: float = 1.0,
-               shared_freqs: bool = False, se3: bool = True) -> PackedReps:
+               shared_freqs: bool = False, se3: bool = True, t2: bool = False, euclid: bool = False) -> PackedReps:
     """Device-side pre_compute_reps (reference: source/encoder.py:183-265, source/decoder.py:247-353).
     extr_* [B,N,4,4], coord_* [B,T,2] (or [B,N,t,2])."""
     dev = extr_k.device
@@ -69,6 +69,12 @@ def build_reps(extr_q: torch.Tensor, extr_k: torch.Tensor, coord_q: torch.Tensor
                                float(max_freq_h), float(max_freq_w), int(shared_freqs), int(so3_maxdeg),
                                _ptr(r.se3_q), _ptr(r.se3_k), _ptr(r.so3_q), _ptr(r.so3_k), _ptr(r.so2_q),
                                _ptr(r.so2_k), _stream()), "gta_build_reps")
+    if euclid and se3:          # the euclid branch multiplies the query points by inv(E_q) itself (gta.py:140,153)
+        r.se3_qi = r.se3_k if same else f(B, Nq, 16)
+        if not same:
+            check(lib().gta_se3_inverse(_ptr(eq), B * Nq, _ptr(r.se3_qi), _stream()), "gta_se3_inverse")
+    if t2:                      # make_T2mats needs nothing but the coordinates (gta.py:72-89)
+        r.t2_q, r.t2_k = cq, ck
     return r
 
 
@@ -85,7 +91,7 @@ def _workspace(dev, nbytes: int) -> torch.Tensor:
     return ws
 
 
-def _params(q, k, v, out, reps: PackedReps, f_dims, trans_coeff, scale, v_transform, flags, lse=None):
+def _params(q, k, v, out, reps: PackedReps, f_dims, trans_coeff, scale, v_transform, flags, lse=None, euclid=False):
     assert q.is_cuda and k.is_cuda and v.is_cuda, "gta_b200 runs on CUDA devices only"
     assert q.dtype == k.dtype == v.dtype and q.dtype in _DT, "q/k/v must all be bf16 or all fp32"
     B, H, Tq, D = q.shape
@@ -102,9 +108,8 @@ def _params(q, k, v, out, reps: PackedReps, f_dims, trans_coeff, scale, v_transf
     p.lse = _ptr(lse)
     p.B, p.H, p.Tq, p.Tk, p.D = B, H, Tq, Tk, D
     p.Nq, p.Nk = reps.n_q_views, reps.n_k_views
-    p.triv, p.se3, p.so3, p.so2 = g("triv"), g("se3"), g("so3"), g("so2")
-    if g("t2"):
-        raise NotImplementedError("gta_b200: the t2 block is not implemented")
+    p.triv, p.se3, p.so3, p.so2, p.t2 = g("triv"), g("se3"), g("so3"), g("so2"), g("t2")
+    p.euclid = int(bool(euclid))
     p.reps = reps.c_struct()
     p.trans_coeff = _ptr(trans_coeff)
     p.scale = float(scale)
@@ -118,7 +123,8 @@ def _params(q, k, v, out, reps: PackedReps, f_dims, trans_coeff, scale, v_transf
 def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: PackedReps, f_dims: dict, *,
                       trans_coeff: Optional[torch.Tensor] = None, scale: Optional[float] = None,
                       v_transform: bool = True, out_dtype: Optional[torch.dtype] = None,
-                      return_lse: bool = False, flags: int = 0, debug_clocks: Optional[torch.Tensor] = None):
+                      return_lse: bool = False, flags: int = 0, debug_clocks: Optional[torch.Tensor] = None,
+                      euclid: bool = False):
     """q [B,H,Tq,D], k,v [B,H,Tk,D] (strided views allowed) -> out [B,H,Tq,D] as a permuted view of a
     contiguous [B,Tq,H,D] buffer (so the reference's 'b h n d -> b n (h d)' is free)."""
     B, H, Tq, D = q.shape
@@ -129,8 +135,8 @@ def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: P
         trans_coeff = trans_coeff.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
     out = torch.empty(B, Tq, H, D, device=dev, dtype=out_dtype or q.dtype)
     lse = torch.empty(B, H, Tq, device=dev, dtype=torch.float32) if return_lse else None
-    p = _params(q, k, v, out, reps, f_dims, trans_coeff, scale, v_transform, flags, lse)
-    nbytes = lib().gta_attn_fwd_workspace_bytes_ex(B, H, k.shape[2], D, p.in_dtype, p.flags)
+    p = _params(q, k, v, out, reps, f_dims, trans_coeff, scale, v_transform, flags, lse, euclid)
+    nbytes = lib().gta_attn_fwd_workspace_bytes_p(p)
     ws = _workspace(dev, nbytes)
     base = ws.data_ptr()
     p.workspace = (base + 1023) // 1024 * 1024
@@ -141,7 +147,7 @@ def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: P
     return (res, lse) if return_lse else res
 
 
-def rotate_debug(q, k, v, reps: PackedReps, f_dims: dict, *, trans_coeff=None, v_transform=True):
+def rotate_debug(q, k, v, reps: PackedReps, f_dims: dict, *, trans_coeff=None, v_transform=True, euclid=False):
     """fp32 rotated operands (q', k', v') as contiguous [B,H,T,D] tensors — for tests."""
     dev = q.device
     if trans_coeff is not None:
@@ -152,7 +158,7 @@ def rotate_debug(q, k, v, reps: PackedReps, f_dims: dict, *, trans_coeff=None, v
     kt = torch.empty(B, H, Tk, D, device=dev, dtype=torch.float32)
     vt = torch.empty(B, H, Tk, D, device=dev, dtype=torch.float32)
     dummy = torch.empty(16, device=dev, dtype=q.dtype)
-    p = _params(q, k, v, dummy, reps, f_dims, trans_coeff, 1.0, v_transform, 0)
+    p = _params(q, k, v, dummy, reps, f_dims, trans_coeff, 1.0, v_transform, 0, euclid=euclid)
     check(lib().gta_rotate_debug(p, _ptr(qt), _ptr(kt), _ptr(vt), _stream()), "gta_rotate_debug")
     return qt, kt, vt
 
@@ -165,6 +171,27 @@ def so2_mats(coord: torch.Tensor, nfreqs: int, max_freqs=(1, 1), shared_freqs: b
     check(lib().gta_so2_mats(_ptr(c), c.shape[0], int(nfreqs), float(max_freqs[0]), float(max_freqs[1]),
                              int(shared_freqs), _ptr(out), _stream()), "gta_so2_mats")
     return out.reshape(*coord.shape[:-1], 2 * nfreqs, 2, 2)
+
+
+def t2_mats(coord: torch.Tensor, with_inverse: bool = False):
+    """[..., 2] -> [..., 3, 3] = [[1,0,0],[0,1,0],[x,y,1]] (make_T2mats, source/utils/gta.py:72-89), optionally with
+    the inverses the callers obtain from torch.linalg.inv (source/encoder.py:212)."""
+    assert coord.is_cuda and coord.shape[-1] == 2
+    c = _f32c(coord).reshape(-1, 2)
+    m = torch.empty(c.shape[0], 3, 3, device=c.device, dtype=torch.float32)
+    mi = torch.empty_like(m) if with_inverse else None
+    check(lib().gta_t2_mats(_ptr(c), c.shape[0], _ptr(m), _ptr(mi), _stream()), "gta_t2_mats")
+    m = m.reshape(*coord.shape[:-1], 3, 3)
+    return (m, mi.reshape(*coord.shape[:-1], 3, 3)) if with_inverse else m
+
+
+def se3_inverse(extr: torch.Tensor) -> torch.Tensor:
+    """[..., 4, 4] -> inverse (torch.linalg.inv at source/encoder.py:219), fp64 Gauss-Jordan on the device."""
+    assert extr.is_cuda and extr.shape[-2:] == (4, 4)
+    e = _f32c(extr).reshape(-1, 16)
+    out = torch.empty_like(e)
+    check(lib().gta_se3_inverse(_ptr(e), e.shape[0], _ptr(out), _stream()), "gta_se3_inverse")
+    return out.reshape(extr.shape)
 
 
 def wigner_d(R: torch.Tensor):

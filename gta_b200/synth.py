@@ -26,13 +26,14 @@ class GtaConfig:
     """Static description of one GTA attention call (mirrors attn_args.method.args of the YAMLs)."""
     heads: int
     head_dim: int
-    f_dims: Dict[str, int]          # order inside a head is fixed: triv | se3 | so3 | so2 (gta.py:115)
+    f_dims: Dict[str, int]          # order inside a head is fixed: triv | se3 | so3 | so2 | t2 (gta.py:115)
     so2: int = 0                    # number of SO(2) frequencies per coordinate axis
     so3: int = 0                    # max Wigner-D degree (only 2 is used by the shipped configs)
     max_freq_h: float = 1.0
     max_freq_w: float = 1.0
     shared_freqs: bool = False
     v_transform: bool = True
+    euclid: bool = False            # euclid_sim: se3 block = homogenised 3-vectors, similarity -|q'-k'|^2/2 (layers.py:213-231)
     n_q_views: int = 1
     n_k_views: int = 1
     name: str = ""
@@ -41,10 +42,14 @@ class GtaConfig:
         g = lambda k: int(self.f_dims.get(k, 0) or 0)
         return g("triv"), g("se3"), g("so3"), g("so2")
 
+    def t2_dim(self):
+        return int(self.f_dims.get("t2", 0) or 0)
+
     def validate(self):
         triv, se3, so3, so2 = self.dims()
-        assert triv + se3 + so3 + so2 == self.head_dim, "f_dims must sum to head_dim"
-        assert se3 % 4 == 0 and so3 % 8 == 0 and so2 % 2 == 0
+        t2 = self.t2_dim()
+        assert triv + se3 + so3 + so2 + t2 == self.head_dim, "f_dims must sum to head_dim"
+        assert se3 % (3 if self.euclid else 4) == 0 and so3 % 8 == 0 and so2 % 2 == 0 and t2 % 3 == 0
         if so2:
             assert so2 == 4 * self.so2, "so2 dims must equal 2 axes * nfreqs * 2"
         if so3:
@@ -56,6 +61,11 @@ MSN_SO3 = dict(heads=8, head_dim=96, f_dims={"triv": 0, "se3": 48, "so3": 24, "s
 CLEVR = dict(heads=6, head_dim=64, f_dims={"se3": 32, "so2": 32}, so2=8, so3=0)
 CFG1_A = dict(heads=4, head_dim=32, f_dims={"se3": 16, "so2": 16}, so2=4, so3=0)
 CFG1_B = dict(heads=4, head_dim=32, f_dims={"se3": 16, "so3": 8, "so2": 8}, so2=2, so3=2)
+# ablation configs served by the generic path (runs/clevrtr/GTA/gta_t2, gta_euclid; runs/msn/GTA/gta_t2, gta_so3_euclid)
+CLEVR_T2 = dict(heads=6, head_dim=64, f_dims={"triv": 2, "se3": 32, "t2": 30}, so2=0, so3=0)
+CLEVR_EUCLID = dict(heads=6, head_dim=64, f_dims={"triv": 2, "se3": 30, "so2": 32}, so2=8, so3=0, euclid=True)
+MSN_T2 = dict(heads=8, head_dim=96, f_dims={"triv": 0, "se3": 48, "t2": 48}, so2=0, so3=0)
+MSN_SO3_EUCLID = dict(heads=8, head_dim=96, f_dims={"triv": 0, "se3": 48, "so3": 24, "so2": 24}, so2=6, so3=2, euclid=True)
 
 
 def make_2dcoord(H: int, W: int) -> np.ndarray:

@@ -68,11 +68,13 @@ def load():
 class _AttnFn:
     """softmax(q k^T * scale / tau) v — what AttnFn.forward computes (source/layers.py:207-211)."""
 
-    def __init__(self, scale, tau=1.0):
-        self.scale, self.tau = scale, tau
+    def __init__(self, scale, tau=1.0, euclid=False):
+        self.scale, self.tau, self.euclid = scale, tau, euclid
 
     def __call__(self, q, k, v):
         sim = q @ k.transpose(-1, -2)
+        if self.euclid:   # EuclidAttnFn.forward (source/layers.py:219-223), also local to Attention.__init__
+            sim = sim - 0.5 * q.pow(2).sum(-1)[..., None] - 0.5 * k.pow(2).sum(-1)[..., None, :]
         attn = torch.softmax(sim * self.scale / self.tau, dim=-1)
         return attn @ v, attn
 
@@ -80,6 +82,13 @@ class _AttnFn:
 def attn_args(cfg):
     a = dict(f_dims=dict(cfg.f_dims), so2=cfg.so2, so3=cfg.so3, max_freq_h=cfg.max_freq_h,
              max_freq_w=cfg.max_freq_w, shared_freqs=cfg.shared_freqs)
+    if not a["f_dims"].get("so2"):
+        # The reference's pre_compute_reps only defines `NqTq` inside its so2 branch and then uses it in the se3
+        # branch (encoder.py:196,238-242): without an so2 block (runs/*/GTA/gta_t2) it raises UnboundLocalError.
+        # For REP CONSTRUCTION ONLY, ask for a one-frequency so2 table as well; the attention call still gets the
+        # real f_dims, so the extra table is never read.
+        a["f_dims"]["so2"] = 4
+        a["so2"] = 1
     return a
 
 
@@ -107,9 +116,9 @@ def ref_gta_attention(cfg, inp, trans_coeff=0.01, tau=1.0, dtype=torch.float32):
     cross = inp["extr_q"] is not inp["extr_k"]
     c = lambda t: t.to(dtype)
     extras = ref_reps(cfg, c(inp["extr_q"]), c(inp["extr_k"]), c(inp["coord_q"]), c(inp["coord_k"]), cross)
-    fn = _AttnFn(cfg.head_dim ** -0.5, tau)
+    fn = _AttnFn(cfg.head_dim ** -0.5, tau, euclid=getattr(cfg, "euclid", False))
     tc = torch.tensor([trans_coeff], dtype=dtype)
     out, attn = m.gta.multihead_geometric_transform_attention(
         c(inp["q"]), c(inp["k"]), c(inp["v"]), attn_fn=fn, f_dims=dict(cfg.f_dims), reps=extras,
-        trans_coeff=tc, v_transform=cfg.v_transform, euclid=False)
+        trans_coeff=tc, v_transform=cfg.v_transform, euclid=getattr(cfg, "euclid", False))
     return out, extras

@@ -96,6 +96,11 @@ def build_reps(cfg, extr_q, extr_k, coord_q, coord_k) -> Dict[str, torch.Tensor]
         mf = [cfg.max_freq_h, cfg.max_freq_w]
         r["so2_th_q"] = so2_angles(coord_q, cfg.so2, mf, cfg.shared_freqs)   # [B,T,2n]
         r["so2_th_k"] = so2_angles(coord_k, cfg.so2, mf, cfg.shared_freqs)
+    if se3 and getattr(cfg, "euclid", False):
+        r["se3_q"] = torch.linalg.inv(extr_q)          # se3rep_q, encoder.py:235 (used un-transposed by the euclid branch)
+    if cfg.t2_dim():
+        r["t2_q"], r["t2_k"] = t2_mats(coord_q), t2_mats(coord_k)             # encoder.py:208-213
+        r["t2_qinv"] = torch.linalg.inv(r["t2_q"])
     return r
 
 
@@ -112,16 +117,31 @@ def _per_view(x: torch.Tensor, N: int) -> torch.Tensor:
     return x.reshape(B, H, N, T // N, C)
 
 
-def _apply_blocks(x, cfg, se3_mat, d1, d2, th, inverse_so2: bool, N: int):
+def t2_mats(coord: torch.Tensor) -> torch.Tensor:
+    """[[1,0,0],[0,1,0],[x,y,1]] per token (make_T2mats, gta.py:72-89)."""
+    m = torch.eye(3, dtype=coord.dtype, device=coord.device).repeat(*coord.shape[:-1], 1, 1)
+    m[..., 2, 0] = coord[..., 0]
+    m[..., 2, 1] = coord[..., 1]
+    return m
+
+
+def _apply_blocks(x, cfg, se3_mat, d1, d2, th, inverse_so2: bool, N: int, t2_mat=None):
     """Block-diagonal rep applied to x [B,H,T,D]; se3_mat [B,N,4,4], d1 [B,N,3,3], d2 [B,N,5,5],
-    th [B,T,C] (gta.py:127-242 for q/k/v, :246-276 for the output)."""
+    th [B,T,C], t2_mat [B,T,3,3] (gta.py:127-242 for q/k/v, :246-276 for the output)."""
     triv, se3, so3, so2 = cfg.dims()
+    t2 = cfg.t2_dim()
     B, H, T, D = x.shape
     parts: List[torch.Tensor] = []
     o = 0
     if triv:
         parts.append(x[..., :triv]); o += triv
-    if se3:
+    if se3 and getattr(cfg, "euclid", False):
+        # homogenised 3-vectors; the appended coordinate is dropped again (gta.py:146-156, 251-253)
+        xs = _per_view(x[..., o:o + se3], N).reshape(B, H, N, T // N, se3 // 3, 3)
+        xs = torch.cat([xs, torch.ones_like(xs[..., :1])], -1)
+        ys = torch.einsum("bnij,bhntcj->bhntci", se3_mat, xs)[..., :-1]
+        parts.append(ys.reshape(B, H, T, se3)); o += se3
+    elif se3:
         xs = _per_view(x[..., o:o + se3], N).reshape(B, H, N, T // N, se3 // 4, 4)
         ys = torch.einsum("bnij,bhntcj->bhntci", se3_mat, xs)
         parts.append(ys.reshape(B, H, T, se3)); o += se3
@@ -138,6 +158,10 @@ def _apply_blocks(x, cfg, se3_mat, d1, d2, th, inverse_so2: bool, N: int):
         y0 = c * xs[..., 0] - s * xs[..., 1]
         y1 = s * xs[..., 0] + c * xs[..., 1]
         parts.append(torch.stack([y0, y1], -1).reshape(B, H, T, so2)); o += so2
+    if t2:
+        xs = x[..., o:o + t2].reshape(B, H, T, t2 // 3, 3)
+        ys = torch.einsum("btij,bhtcj->bhtci", t2_mat, xs)                    # t2fn, encoder.py:214
+        parts.append(ys.reshape(B, H, T, t2)); o += t2
     return torch.cat(parts, -1)
 
 
@@ -146,13 +170,17 @@ def transform_qkv(cfg, q, k, v, reps, trans_coeff):
     triv, se3, so3, so2 = cfg.dims()
     Nq, Nk = cfg.n_q_views, cfg.n_k_views
     Aq = Ak = None
-    if se3:
+    if se3 and getattr(cfg, "euclid", False):
+        Aq = _scale_translation(reps["se3_q"], trans_coeff)                        # c_q, gta.py:140,153
+        Ak = _scale_translation(reps["se3_k"], trans_coeff)
+    elif se3:
         Aq = _scale_translation(reps["se3_qinv"], trans_coeff).transpose(-1, -2)   # gta.py:165
         Ak = _scale_translation(reps["se3_k"], trans_coeff)                        # gta.py:166
     d = lambda n: reps.get(n)
-    qt = _apply_blocks(q, cfg, Aq, d("so3_d1_q"), d("so3_d2_q"), d("so2_th_q"), False, Nq)
-    kt = _apply_blocks(k, cfg, Ak, d("so3_d1_k"), d("so3_d2_k"), d("so2_th_k"), False, Nk)
-    vt = _apply_blocks(v, cfg, Ak, d("so3_d1_k"), d("so3_d2_k"), d("so2_th_k"), False, Nk) \
+    t2q = reps["t2_qinv"].transpose(-1, -2) if cfg.t2_dim() else None              # gta.py:233
+    qt = _apply_blocks(q, cfg, Aq, d("so3_d1_q"), d("so3_d2_q"), d("so2_th_q"), False, Nq, t2q)
+    kt = _apply_blocks(k, cfg, Ak, d("so3_d1_k"), d("so3_d2_k"), d("so2_th_k"), False, Nk, d("t2_k"))
+    vt = _apply_blocks(v, cfg, Ak, d("so3_d1_k"), d("so3_d2_k"), d("so2_th_k"), False, Nk, d("t2_k")) \
         if cfg.v_transform else v
     return qt, kt, vt
 
@@ -165,6 +193,8 @@ def gta_attention(cfg, q, k, v, extr_q, extr_k, coord_q, coord_k, trans_coeff=0.
     qt, kt, vt = transform_qkv(cfg, q, k, v, reps, trans_coeff)
     scale = cfg.head_dim ** -0.5
     sim = qt @ kt.transpose(-1, -2)
+    if getattr(cfg, "euclid", False):          # EuclidAttnFn, layers.py:219-223
+        sim = sim - 0.5 * qt.pow(2).sum(-1)[..., None] - 0.5 * kt.pow(2).sum(-1)[..., None, :]
     attn = torch.softmax(sim * (scale / tau), dim=-1)
     out = attn @ vt
     if not cfg.v_transform:
@@ -173,7 +203,7 @@ def gta_attention(cfg, q, k, v, extr_q, extr_k, coord_q, coord_k, trans_coeff=0.
     Ao = _scale_translation(reps["se3_qinv"], trans_coeff) if se3 else None         # gta.py:255-257
     d1t = reps["so3_d1_q"].transpose(-1, -2) if so3 else None                       # gta.py:188
     d2t = reps["so3_d2_q"].transpose(-1, -2) if so3 else None
-    return _apply_blocks(out, cfg, Ao, d1t, d2t, reps.get("so2_th_q"), True, cfg.n_q_views)
+    return _apply_blocks(out, cfg, Ao, d1t, d2t, reps.get("so2_th_q"), True, cfg.n_q_views, reps.get("t2_qinv"))
 
 
 def so2_mats(th: torch.Tensor) -> torch.Tensor:

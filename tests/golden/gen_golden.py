@@ -15,7 +15,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-from gta_b200.synth import CFG1_A, CFG1_B, CLEVR, MSN_SO3, GtaConfig, make_inputs  # noqa: E402
+from gta_b200.synth import (CFG1_A, CFG1_B, CLEVR, CLEVR_EUCLID, CLEVR_T2, MSN_SO3, MSN_SO3_EUCLID, MSN_T2,  # noqa: E402
+                            GtaConfig, make_inputs)
 from oracle import ref_harness as rh  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -28,6 +29,14 @@ CASES = [
     ("msn_self_tc1", MSN_SO3, 5, 5, 4, 4, False, 1, 1.0, 14, True),
     ("clevr_self_ragged", CLEVR, 2, 2, 21, 21, False, 1, 0.01, 15, True),
     ("clevr_cross_novt", CLEVR, 3, 2, 7, 12, True, 1, 0.01, 16, False),
+]
+# ablation configs (t2 block, euclid_sim, blocks that are not multiples of 8): same tuple layout
+ABLATION_CASES = [
+    ("clevr_t2_self", CLEVR_T2, 2, 2, 21, 21, False, 1, 0.01, 31, True),
+    ("msn_t2_cross_tc1", MSN_T2, 3, 2, 8, 16, True, 1, 1.0, 32, True),
+    ("clevr_euclid_self", CLEVR_EUCLID, 2, 2, 21, 21, False, 1, 0.01, 33, True),
+    ("msn_so3_euclid_cross", MSN_SO3_EUCLID, 3, 2, 8, 16, True, 1, 0.3, 34, True),
+    ("clevr_euclid_cross_novt", CLEVR_EUCLID, 3, 2, 7, 12, True, 1, 0.01, 35, False),
 ]
 
 
@@ -53,7 +62,7 @@ def gimbal_extrinsics():
 
 
 def main():
-    for name, base, nq, nk, tq, tk, cross, B, tc, seed, vt in CASES:
+    for name, base, nq, nk, tq, tk, cross, B, tc, seed, vt in CASES + ABLATION_CASES:
         cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk, v_transform=vt)
         inp = make_inputs(cfg, B, tq, tk, cross=cross, seed=seed)
         out, ex = rh.ref_gta_attention(cfg, inp, trans_coeff=tc)
@@ -61,7 +70,7 @@ def main():
         d["out"] = out.contiguous().numpy()
         d["trans_coeff"] = np.float32(tc)
         d["cross"] = np.int32(cross)
-        for key in ("se3rep_q", "se3rep_k", "inv_se3rep_q", "so2rep_q", "so2rep_k"):
+        for key in ("se3rep_q", "se3rep_k", "inv_se3rep_q", "so2rep_q", "so2rep_k", "t2rep_q", "t2rep_k", "inv_t2rep_q"):
             if key in ex:
                 d["ref_" + key] = ex[key].contiguous().numpy()
         for key in ("so3rep_q", "so3rep_k"):

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     l = _lib.lib()
     for name in _declared_symbols():
         assert hasattr(l, name), name
-    assert l.gta_abi_version() == 1
+    assert l.gta_abi_version() == 2
 
 
 def test_struct_layout_matches_header_order():
@@ -51,6 +51,12 @@ def test_workspace_bytes():
     assert l.gta_attn_fwd_workspace_bytes(2, 8, 1280, 96) == 2 * 2 * 8 * 10 * 128 * 96 * 2
     assert l.gta_attn_fwd_workspace_bytes(1, 6, 600, 64) == 2 * 6 * 5 * 128 * 64 * 2
     assert l.gta_attn_fwd_workspace_bytes(0, 6, 600, 64) == 0
+    p = _params(B=2, H=8, Tk=1280, Tq=1280, D=96, se3=48, so3=24, so2=24)
+    assert l.gta_attn_fwd_workspace_bytes_p(ctypes.byref(p)) == l.gta_attn_fwd_workspace_bytes(2, 8, 1280, 96)
+    # generic path (t2 block): dense Q', K', V' (bf16), fp32 O', then the tile images
+    g = _params(B=1, H=6, Tq=600, Tk=600, D=64, triv=2, se3=32, so3=0, so2=0, t2=30)
+    dense = 3 * ((6 * 600 * 64 * 2 + 1023) // 1024 * 1024) + (6 * 600 * 64 * 4 + 1023) // 1024 * 1024
+    assert l.gta_attn_fwd_workspace_bytes_p(ctypes.byref(g)) == dense + l.gta_attn_fwd_workspace_bytes(1, 6, 600, 64)
 
 
 def _params(**over):
@@ -60,7 +66,7 @@ def _params(**over):
     p.B, p.H, p.Tq, p.Tk, p.D = 1, 2, 16, 16, 32
     p.Nq = p.Nk = 2
     p.triv, p.se3, p.so3, p.so2 = 0, 16, 8, 8
-    p.reps = _lib.GtaReps(dummy, dummy, dummy, dummy, dummy, dummy)
+    p.reps = _lib.GtaReps(dummy, dummy, dummy, dummy, dummy, dummy, None, None, None)
     p.q_stride_b = p.k_stride_b = p.v_stride_b = 16 * 2 * 32
     p.q_stride_h = p.k_stride_h = p.v_stride_h = 32
     p.q_stride_t = p.k_stride_t = p.v_stride_t = 64
@@ -73,7 +79,11 @@ def _params(**over):
 
 @pytest.mark.parametrize("over,code,msg", [
     (dict(D=48), -3, "head dim"),
-    (dict(se3=20, so3=4), -3, "multiple of 8"),
+    (dict(se3=20, so3=4), -1, "whole"),
+    (dict(se3=18, so3=0, so2=14), -1, "whole"),
+    (dict(se3=15, so3=8, so2=0, euclid=1, D=96, triv=73), -1, "se3_qi"),
+    (dict(se3=12, so3=8, so2=6, t2=6), -1, "t2 coordinates"),
+    (dict(D=128, se3=0, so3=0, so2=0, triv=128, euclid=1), -3, "euclid_sim"),
     (dict(se3=24), -1, "sum to head dim"),
     (dict(Tq=15), -1, "divisible"),
     (dict(q=None), -1, "null"),

@@ -12,7 +12,8 @@ import numpy as np
 import pytest
 import torch
 
-from gta_b200.synth import CFG1_A, CFG1_B, CLEVR, MSN_SO3, GtaConfig, make_inputs
+from gta_b200.synth import (CFG1_A, CFG1_B, CLEVR, CLEVR_EUCLID, CLEVR_T2, MSN_SO3, MSN_SO3_EUCLID, MSN_T2, GtaConfig,
+                            make_inputs)
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -30,7 +31,8 @@ def _dev_reps(cfg, inp):
     eq = ek if inp["extr_q"] is inp["extr_k"] else inp["extr_q"].cuda()
     cq = ck if inp["coord_q"] is inp["coord_k"] else inp["coord_q"].cuda()
     return ops.build_reps(eq, ek, cq, ck, so2_nfreqs=cfg.so2, so3_maxdeg=cfg.so3, max_freq_h=cfg.max_freq_h,
-                          max_freq_w=cfg.max_freq_w, shared_freqs=cfg.shared_freqs)
+                          max_freq_w=cfg.max_freq_w, shared_freqs=cfg.shared_freqs, t2=bool(cfg.t2_dim()),
+                          euclid=cfg.euclid)
 
 
 def _run(cfg, inp, tc=0.01, flags=0, out_dtype=None):
@@ -38,12 +40,17 @@ def _run(cfg, inp, tc=0.01, flags=0, out_dtype=None):
     reps = _dev_reps(cfg, inp)
     out = ops.gta_attention_fwd(inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), reps, cfg.f_dims,
                                 trans_coeff=torch.tensor([tc], device="cuda"), v_transform=cfg.v_transform,
-                                flags=flags, out_dtype=out_dtype)
+                                flags=flags, out_dtype=out_dtype, euclid=cfg.euclid)
     torch.cuda.synchronize()
     return out.float().cpu().numpy()
 
 
 def _oracle(cfg, inp, tc=0.01):
+    if cfg.euclid or cfg.t2_dim():       # ablation blocks: the torch restatement (fp64) is the checker
+        from oracle import torch_port as tp
+        d = lambda t: t.double()
+        return tp.gta_attention(cfg, d(inp["q"]), d(inp["k"]), d(inp["v"]), d(inp["extr_q"]), d(inp["extr_k"]),
+                                d(inp["coord_q"]), d(inp["coord_k"]), trans_coeff=tc).float().numpy()
     from oracle import c_oracle
     return c_oracle.gta_attention(cfg, inp["q"].float(), inp["k"].float(), inp["v"].float(), inp["extr_q"],
                                   inp["extr_k"], inp["coord_q"], inp["coord_k"], trans_coeff=tc)
@@ -115,8 +122,37 @@ def test_rotated_operands_match_oracle(dtype):
         assert np.abs(a.cpu().numpy() - b).max() < 5e-6
 
 
-@pytest.mark.parametrize("name", sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                                        if "reps_" not in p))
+def _golden_names(ablation):
+    from tests.golden.gen_golden import ABLATION_CASES, CASES
+    return [c[0] for c in (ABLATION_CASES if ablation else CASES)]
+
+
+@pytest.mark.parametrize("name", _golden_names(True))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_golden_vectors_ablation_blocks(name, dtype):
+    """t2 block / euclid_sim / head layouts with blocks that are not multiples of 8 (generic path) against the committed
+    outputs of the unmodified reference."""
+    from tests.golden.gen_golden import ABLATION_CASES
+    _, base, nq, nk, tq, tk, cross, B, tc, seed, vt = [c for c in ABLATION_CASES if c[0] == name][0]
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk, v_transform=vt)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    inp = {k: torch.from_numpy(g[k]) for k in ("q", "k", "v", "extr_q", "extr_k", "coord_q", "coord_k")}
+    if not cross:
+        inp["extr_q"], inp["coord_q"] = inp["extr_k"], inp["coord_k"]
+    if dtype == torch.bfloat16:
+        inp = dict(inp, **{n: inp[n].to(dtype) for n in "qkv"})
+        ref = _oracle(cfg, inp, float(g["trans_coeff"]))          # same (rounded) inputs
+    else:
+        ref = g["out"]
+    out = _run(cfg, inp, tc=float(g["trans_coeff"]))
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() < _tol(ref, float(g["trans_coeff"]))
+    if dtype == torch.float32 and cfg.head_dim + (32 if cfg.euclid else 0) <= 96:
+        # split-precision tensor-core path: fp32 budget (relative to the output scale when trans_coeff = 1)
+        assert np.abs(out - ref).max() < 1e-3 * max(1.0, float(np.abs(ref).max()))
+
+
+@pytest.mark.parametrize("name", _golden_names(False))
 @pytest.mark.parametrize("flags", [0, 256, 32, 64, 16, 8, 9], ids=["v5", "v3", "v2", "v4", "v1", "v0_P_smem", "v0_P_tmem"])
 def test_golden_vectors(name, flags):
     """Committed outputs of the unmodified reference (fp32, CPU) vs the fused kernel fed the same fp32 inputs."""
@@ -298,6 +334,61 @@ def test_dropin_signature_with_reference_format_reps():
     ref = _oracle(cfg, inp)
     assert np.abs(out.float().cpu().numpy() - ref).max() < _tol(ref)
     assert "_gta_b200_packed" in extras      # packed once, reused by the next layer
-    with pytest.raises(NotImplementedError):
-        fast.multihead_geometric_transform_attention(inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), AttnFn(),
-                                                     cfg.f_dims, extras, trans_coeff=tc, euclid=True)
+    # euclid_sim through the same signature (se3 = 48 = 16 homogenised 3-vectors; needs extras['se3rep_q'])
+    cfg_e = GtaConfig(**MSN_SO3_EUCLID, n_q_views=3, n_k_views=2)
+    with torch.no_grad():
+        out_e, _ = fast.multihead_geometric_transform_attention(
+            inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), AttnFn(), cfg_e.f_dims, extras, trans_coeff=tc, euclid=True)
+    ref_e = _oracle(cfg_e, inp)
+    assert np.abs(out_e.float().cpu().numpy() - ref_e).max() < _tol(ref_e)
+
+
+def test_dropin_t2_reference_format_reps():
+    """t2 block fed the reference-format [B,T,3,3] matrices (make_T2mats / torch.linalg.inv, encoder.py:208-215)."""
+    from gta_b200 import gta as fast
+    cfg = GtaConfig(**CLEVR_T2, n_q_views=3, n_k_views=2)
+    inp = make_inputs(cfg, 2, 40, 64, cross=True, seed=18, dtype=torch.bfloat16)
+    t2q, t2k = fast.make_T2mats(inp["coord_q"].cuda()), fast.make_T2mats(inp["coord_k"].cuda())
+    from oracle import torch_port as tp
+    assert (t2q.cpu() - tp.t2_mats(inp["coord_q"])).abs().max() == 0
+    extras = {"se3rep_q": torch.linalg.inv(inp["extr_q"]).cuda(), "se3rep_k": torch.linalg.inv(inp["extr_k"]).cuda(),
+              "inv_se3rep_q": inp["extr_q"].cuda(), "t2rep_q": t2q, "t2rep_k": t2k, "inv_t2rep_q": torch.linalg.inv(t2q)}
+
+    class AttnFn:
+        scale = cfg.head_dim ** -0.5
+    with torch.no_grad():
+        out, _ = fast.multihead_geometric_transform_attention(
+            inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), AttnFn(), cfg.f_dims, extras,
+            trans_coeff=torch.tensor([0.01], device="cuda"))
+    ref = _oracle(cfg, inp)
+    assert np.abs(out.float().cpu().numpy() - ref).max() < _tol(ref)
+
+
+@pytest.mark.parametrize("case", [
+    (CLEVR_T2, 2, 2, 300, 300, False, 2, torch.bfloat16, 0.01), (CLEVR_EUCLID, 3, 2, 853, 300, True, 1, torch.bfloat16, 0.01),
+    (MSN_T2, 5, 5, 256, 256, False, 1, torch.bfloat16, 0.01), (MSN_SO3_EUCLID, 5, 5, 256, 256, False, 1, torch.bfloat16, 0.01),
+    (MSN_SO3_EUCLID, 5, 5, 128, 256, True, 1, torch.float32, 0.3), (CLEVR_EUCLID, 2, 2, 300, 300, False, 1, torch.float32, 1.0),
+], ids=["clevr_t2_enc", "clevr_euclid_dec", "msn_t2_enc", "msn_so3_euclid_enc", "msn_so3_euclid_f32", "clevr_euclid_f32_tc1"])
+def test_ablation_blocks_at_model_shapes(case):
+    base, nq, nk, tq, tk, cross, B, dtype, tc = case
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
+    inp = make_inputs(cfg, B, tq, tk, cross=cross, seed=19, dtype=dtype)
+    ref = _oracle(cfg, inp, tc)
+    out = _run(cfg, inp, tc)
+    assert np.isfinite(out).all()
+    assert np.abs(out - ref).max() < _tol(ref, tc)
+
+
+def test_generic_rotated_operands_match_oracle():
+    from oracle import torch_port as tp
+    ops = _ops()
+    for base in (CLEVR_T2, MSN_SO3_EUCLID, CLEVR_EUCLID):
+        cfg = GtaConfig(**base, n_q_views=3, n_k_views=2)
+        inp = make_inputs(cfg, 2, 8, 16, cross=True, seed=2, dtype=torch.float32)
+        reps = _dev_reps(cfg, inp)
+        qt, kt, vt = ops.rotate_debug(inp["q"].cuda(), inp["k"].cuda(), inp["v"].cuda(), reps, cfg.f_dims,
+                                      trans_coeff=torch.tensor([0.3], device="cuda"), euclid=cfg.euclid)
+        r = tp.build_reps(cfg, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"])
+        q2, k2, v2 = tp.transform_qkv(cfg, inp["q"], inp["k"], inp["v"], r, 0.3)
+        for a, b in ((qt, q2), (kt, k2), (vt, v2)):
+            assert (a.cpu() - b).abs().max() < 5e-6

@@ -8,23 +8,24 @@ import numpy as np
 import pytest
 import torch
 
-from gta_b200.synth import CFG1_A, CFG1_B, CLEVR, MSN_SO3, GtaConfig, make_inputs
+from gta_b200.synth import (CFG1_A, CFG1_B, CLEVR, CLEVR_EUCLID, CLEVR_T2, MSN_SO3, MSN_SO3_EUCLID, MSN_T2, GtaConfig,
+                            make_inputs)
 from oracle import c_oracle, ref_harness, torch_port as tp
-from tests.golden.gen_golden import CASES
+from tests.golden.gen_golden import ABLATION_CASES, CASES
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 T = torch.from_numpy
 
 
 def _case(name):
-    for c in CASES:
+    for c in CASES + ABLATION_CASES:
         if c[0] == name:
             _, base, nq, nk, tq, tk, cross, B, tc, seed, vt = c
             return GtaConfig(**base, n_q_views=nq, n_k_views=nk, v_transform=vt), cross
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", [c[0] for c in CASES])
+@pytest.mark.parametrize("name", [c[0] for c in CASES + ABLATION_CASES])
 def test_torch_port_matches_golden(name):
     cfg, cross = _case(name)
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -156,3 +157,19 @@ def test_against_live_reference(base, nq, nk, tq, tk, cross):
     o2 = tp.gta_attention(cfg, inp["q"], inp["k"], inp["v"], inp["extr_q"], inp["extr_k"],
                           inp["coord_q"], inp["coord_k"], trans_coeff=0.3)
     assert (o2 - ref).abs().max() < 2e-6
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("base,nq,nk,tq,tk,cross,vt", [
+    (CLEVR_T2, 2, 2, 30, 30, False, True), (MSN_T2, 3, 2, 8, 16, True, False), (CLEVR_EUCLID, 3, 2, 11, 30, True, True),
+    (MSN_SO3_EUCLID, 5, 5, 16, 16, False, True), (MSN_SO3_EUCLID, 3, 2, 8, 16, True, False)])
+def test_ablation_blocks_against_live_reference(base, nq, nk, tq, tk, cross, vt):
+    """t2 block and euclid_sim: the torch restatement against the unmodified reference function."""
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk, v_transform=vt)
+    inp = make_inputs(cfg, 2, tq, tk, cross=cross, seed=22)
+    ref, ex = ref_harness.ref_gta_attention(cfg, inp, trans_coeff=0.3)
+    o2 = tp.gta_attention(cfg, inp["q"], inp["k"], inp["v"], inp["extr_q"], inp["extr_k"],
+                          inp["coord_q"], inp["coord_k"], trans_coeff=0.3)
+    assert (o2 - ref).abs().max() < 2e-6
+    if cfg.t2_dim():
+        assert (tp.t2_mats(inp["coord_k"]) - ex["t2rep_k"]).abs().max() == 0

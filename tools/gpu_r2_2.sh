@@ -1,8 +1,9 @@
 #!/bin/bash
 # v5 pipeline (four softmax warpgroups, column-split score tiles) bring-up
 mkdir -p gpurun_out
-timeout 240 python __graft_entry__.py smoke 2>&1 | tail -3
-timeout 700 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "v5 or fp32 or strided or lse or identity or invariance or long_sequence or dropin" 2>&1 | tail -6 | tee gpurun_out/pytest_v5.log
+set -o pipefail
+timeout 150 python __graft_entry__.py smoke 2>&1 | tail -3 || { echo 'SMOKE FAILED - stopping'; exit 1; }
+timeout 500 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "v5 or fp32 or strided or lse or identity or invariance or long_sequence or dropin or ablation or generic" 2>&1 | tail -15 | tee gpurun_out/pytest_v5.log || { echo "PYTEST FAILED - stopping"; exit 1; }
 timeout 200 python tools/phase_timing5.py msn_enc 64 2>&1 | tee gpurun_out/phase_v5_msn_enc.log
 bench_one() {  # name, lib, extra args
   local name=$1 lib=$2; shift 2
