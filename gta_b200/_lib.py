@@ -20,9 +20,6 @@ GTA_FLAG_STAGE_ONLY = 4
 GTA_FLAG_V0_PIPELINE = 8
 GTA_FLAG_FAST_FP32 = 128
 GTA_FLAG_V1_PIPELINE = 16
-GTA_FLAG_V2_PIPELINE = 32
-GTA_FLAG_V3_PIPELINE = 256
-GTA_FLAG_V4_PIPELINE = 64
 
 
 class GtaReps(ctypes.Structure):

@@ -35,9 +35,6 @@ int launch_rotate_debug(const GtaAttnParams& p, float* qt, float* kt, float* vt,
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v2(const GtaAttnParams& p, cudaStream_t st);
-int launch_attn_fwd_v3(const GtaAttnParams& p, cudaStream_t st);
-int launch_attn_fwd_v5(const GtaAttnParams& p, cudaStream_t st);
-int launch_attn_fwd_v4(const GtaAttnParams& p, cudaStream_t st);
 int launch_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
                          cudaStream_t st);
 int launch_umma_bench(int D, int mode, int reps, int grid, long long* out, cudaStream_t st);

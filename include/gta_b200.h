@@ -102,9 +102,6 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_FAST_FP32 128 /* fp32 inputs: multiply in plain bf16 (1e-2 budget) instead of the split-precision path */
 #define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 #define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
-#define GTA_FLAG_V2_PIPELINE 32 /* third generation: persistent CTAs, epilogue and Q staging on the softmax / stager warps */
-#define GTA_FLAG_V3_PIPELINE 256 /* experiment: Q staging + epilogue on a fourth warpgroup, output rows bulk-copied from shared memory */
-#define GTA_FLAG_V4_PIPELINE 64 /* experiment: persistent CTAs, S/P decoupled, one UMMA issuer warp per query tile */
 
 /* Scratch for the rotated K'/V' operand tiles (bf16 inputs, or fp32 inputs with GTA_FLAG_FAST_FP32). */
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D);

@@ -153,7 +153,7 @@ def test_golden_vectors_ablation_blocks(name, dtype):
 
 
 @pytest.mark.parametrize("name", _golden_names(False))
-@pytest.mark.parametrize("flags", [0, 256, 32, 64, 16, 8, 9], ids=["v5", "v3", "v2", "v4", "v1", "v0_P_smem", "v0_P_tmem"])
+@pytest.mark.parametrize("flags", [0, 16, 8, 9], ids=["v2", "v1", "v0_P_smem", "v0_P_tmem"])
 def test_golden_vectors(name, flags):
     """Committed outputs of the unmodified reference (fp32, CPU) vs the fused kernel fed the same fp32 inputs."""
     from tests.golden.gen_golden import CASES
@@ -185,7 +185,7 @@ CASES_GPU = [
 
 
 @pytest.mark.parametrize("case", CASES_GPU, ids=lambda c: f"D{c[0]['head_dim']}_{c[1]}x{c[3]}_{c[2]}x{c[4]}_{'x' if c[5] else 's'}_{str(c[7])[6:]}")
-@pytest.mark.parametrize("flags", [0, 256, 32, 64, 16, 8, 9], ids=["v5", "v3", "v2", "v4", "v1", "v0_P_smem", "v0_P_tmem"])
+@pytest.mark.parametrize("flags", [0, 16, 8, 9], ids=["v2", "v1", "v0_P_smem", "v0_P_tmem"])
 def test_fused_attention_matches_oracle(case, flags):
     base, nq, nk, tq, tk, cross, B, dtype, tc = case
     cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
@@ -279,7 +279,7 @@ def test_frame_invariance_and_linearity_full_size():
     assert np.abs(_run(cfg, inp3, out_dtype=torch.float32) - 2 * base).max() < 1e-5
 
 
-@pytest.mark.parametrize("flags", [0, 256, 32, 64], ids=["v5", "v3", "v2", "v4"])
+@pytest.mark.parametrize("flags", [0, 16], ids=["v2", "v1"])
 @pytest.mark.parametrize("case", [(CLEVR, 2, 2, 300, 300, False, 32), (MSN_SO3, 5, 5, 256, 256, False, 24),
                                   (CLEVR, 3, 2, 853, 300, True, 8)],
                          ids=["clevr_enc_B32", "msn_enc_B24", "clevr_dec_B8"])
