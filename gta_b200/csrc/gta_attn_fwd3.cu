@@ -28,9 +28,6 @@ constexpr int kStagerThreads = 64;
 constexpr uint32_t k3TmemSA = 0, k3TmemSB = 128, k3TmemOA = 256, k3TmemOB = 384;
 constexpr float k3RescaleThreshold = 8.0f;   // log2 units
 // Fraction of the exponentials evaluated with poly_exp2x2 instead of MUFU.EX2: pairs with (i % DEN) < NUM.
-#ifndef GTA_LD_SPLIT
-#define GTA_LD_SPLIT 0
-#endif
 #ifndef GTA_POLY_NUM
 #define GTA_POLY_NUM 0
 #endif
@@ -163,53 +160,28 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                 if (dbg) d_wait_s += clock64() - d_w0;
                 tc_fence_after();
                 uint32_t sreg[128];
+                tmem_ld32(s_addr, sreg);
+                tmem_ld32(s_addr + 32, sreg + 32);
+                tmem_ld32(s_addr + 64, sreg + 64);
+                tmem_ld32(s_addr + 96, sreg + 96);
+                tmem_ld_wait();
                 float* s = reinterpret_cast<float*>(sreg);
-                float m_tile;
-                if (GTA_LD_SPLIT && !(j == n - 1 && a.Tk - j * 128 < 128)) {
-                    // two half loads: the row maximum of keys 0..63 is computed while keys 64..127 are still in flight
-                    tmem_ld32(s_addr, sreg);
-                    tmem_ld32(s_addr + 32, sreg + 32);
-                    tmem_ld_wait();
-                    tmem_ld32(s_addr + 64, sreg + 64);
-                    tmem_ld32(s_addr + 96, sreg + 96);
-                    float mx0 = fmax3(s[0], s[1], s[2]), mx1 = fmax3(s[3], s[4], s[5]);
-                    float mx2 = fmax3(s[6], s[7], s[8]), mx3 = fmax3(s[9], s[10], s[11]);
+                if (j == n - 1) {
+                    const int nvalid = a.Tk - j * 128;
+                    if (nvalid < 128) {
 #pragma unroll
-                    for (int i = 12; i < 60; i += 8) {
-                        mx0 = fmax3(mx0, s[i], s[i + 1]); mx1 = fmax3(mx1, s[i + 2], s[i + 3]);
-                        mx2 = fmax3(mx2, s[i + 4], s[i + 5]); mx3 = fmax3(mx3, s[i + 6], s[i + 7]);
+                        for (int i = 0; i < 128; ++i) if (i >= nvalid) s[i] = -INFINITY;
                     }
-                    mx0 = fmax3(mx0, s[60], s[61]); mx1 = fmax3(mx1, s[62], s[63]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 64; i < 128; i += 8) {
-                        mx0 = fmax3(mx0, s[i], s[i + 1]); mx1 = fmax3(mx1, s[i + 2], s[i + 3]);
-                        mx2 = fmax3(mx2, s[i + 4], s[i + 5]); mx3 = fmax3(mx3, s[i + 6], s[i + 7]);
-                    }
-                    m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-                } else {
-                    tmem_ld32(s_addr, sreg);
-                    tmem_ld32(s_addr + 32, sreg + 32);
-                    tmem_ld32(s_addr + 64, sreg + 64);
-                    tmem_ld32(s_addr + 96, sreg + 96);
-                    tmem_ld_wait();
-                    if (j == n - 1) {
-                        const int nvalid = a.Tk - j * 128;
-                        if (nvalid < 128) {
-#pragma unroll
-                            for (int i = 0; i < 128; ++i) if (i >= nvalid) s[i] = -INFINITY;
-                        }
-                    }
-                    float mx0 = fmax3(s[0], s[1], s[2]), mx1 = fmax3(s[3], s[4], s[5]);
-                    float mx2 = fmax3(s[6], s[7], s[8]), mx3 = fmax3(s[9], s[10], s[11]);
-#pragma unroll
-                    for (int i = 12; i < 124; i += 8) {
-                        mx0 = fmax3(mx0, s[i], s[i + 1]); mx1 = fmax3(mx1, s[i + 2], s[i + 3]);
-                        mx2 = fmax3(mx2, s[i + 4], s[i + 5]); mx3 = fmax3(mx3, s[i + 6], s[i + 7]);
-                    }
-                    mx0 = fmax3(mx0, s[124], s[125]); mx1 = fmax3(mx1, s[126], s[127]);
-                    m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 }
+                float mx0 = fmax3(s[0], s[1], s[2]), mx1 = fmax3(s[3], s[4], s[5]);
+                float mx2 = fmax3(s[6], s[7], s[8]), mx3 = fmax3(s[9], s[10], s[11]);
+#pragma unroll
+                for (int i = 12; i < 124; i += 8) {
+                    mx0 = fmax3(mx0, s[i], s[i + 1]); mx1 = fmax3(mx1, s[i + 2], s[i + 3]);
+                    mx2 = fmax3(mx2, s[i + 4], s[i + 5]); mx3 = fmax3(mx3, s[i + 6], s[i + 7]);
+                }
+                mx0 = fmax3(mx0, s[124], s[125]); mx1 = fmax3(mx1, s[126], s[127]);
+                const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 
                 const bool grow = (m_tile - m_used) * cs > k3RescaleThreshold;   // always true on the item's first tile
                 if (__any_sync(0xffffffffu, grow)) {
@@ -261,85 +233,112 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                 mbar_arrive(&bars[L::bPFull + X]);
             }
 
-            // ---- epilogue of this item: drain the whole accumulator row with ONE TMEM round trip (the 128 score registers
-            // are dead here), release O_X at once, then normalise, rotate and store from registers.  (The first version
-            // walked the row 8 columns at a time straight from TMEM: 12 dependent round trips of ~450 clk each under
-            // load made the epilogue 15 % of an item.)  One pass per block type keeps only one kind of rep data live.
+            // ---- epilogue of this item: prefetch the row's reps, drain O to registers, release O, then finish.
             const long long d_t1 = dbg ? clock64() : 0;
             const int t = ic.p * 256 + X * 128 + r;
             const bool valid = t < a.Tq;
             const int tt = valid ? t : a.Tq - 1;
+            // The output rotation walks the head row block type by block type with rolled loops (8 accumulator columns
+            // per step straight from TMEM), so only ONE kind of rep data is live at a time: the view matrices are requested
+            // before the wait for the last PV, the per-token SO(2) entries one chunk ahead of their use.  (A fully
+            // unrolled epilogue kept M, W and all SO(2) chunks live next to 96 accumulator values and spilled ~150
+            // local-memory loads per 32-column block.)
+            const int c_se3 = a.hd.triv >> 3, n_se3 = a.hd.se3 >> 3, c_so3 = c_se3 + n_se3, n_so3 = a.hd.so3 >> 3;
+            const int c_so2 = c_so3 + n_so3;
+            // (all of this row's rep data was pulled into L1 one key tile ago, so each block loads its operands right
+            //  before use and nothing has to stay live across the wait)
             const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
             const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
             mbar_wait(&bars[L::bOFinal + X], cnt & 1);
             const long long d_t2 = dbg ? clock64() : 0;
             ++cnt;
             tc_fence_after();
-            uint32_t oreg[D];
-#pragma unroll
-            for (int c32 = 0; c32 < D / 32; ++c32) tmem_ld32(o_addr + c32 * 32, oreg + c32 * 32);
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(&bars[L::bOFree + X]);                  // O_X is in registers: the next item's PV_X(0) may overwrite it
-            const long long e0 = dbg ? clock64() : 0;
-            float* o = reinterpret_cast<float*>(oreg);
             const float inv_l = 1.0f / l_run;
+            TOut* orow = reinterpret_cast<TOut*>(a.out) + ((static_cast<int64_t>(ic.b) * a.Tq + tt) * a.H + ic.h) * D;
+            // O columns are fetched 8 at a time, one chunk AHEAD of their use (tcgen05.ld is asynchronous until
+            // tcgen05.wait::ld), so the TMEM round trip overlaps the rotation of the previous chunk.
+            uint32_t ocur[8];
+            tmem_ld8(o_addr, ocur);
+            auto next_o = [&](int c, float* x) {          // returns chunk c (already in flight), starts chunk c + 1
+                tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < D; ++i) o[i] *= inv_l;
+                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(ocur[i]) * inv_l;
+                if (c + 1 < D / 8) tmem_ld8(o_addr + (c + 1) * 8, ocur);   // consumed above; in-order issue makes the reuse safe
+            };
+            // 32-byte stores (STG.256): a thread owns a whole 2*D-byte output row, so every 16-byte store is its own
+            // L1/L2 transaction (the v2 epilogue was bound by ~2.5 clk per such transaction); pairing two chunks halves
+            // the transaction count and writes full sectors.  `pend` carries the even chunk across block-type sections.
+            uint4 pend = make_uint4(0, 0, 0, 0);
+            auto emit = [&](int c, const float* x) {
+                if (sizeof(TOut) == 4) {
+                    if (valid)
+                        st_global_v8(orow + c * 8, make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])),
+                                     make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7])));
+                } else {
+                    const uint4 pk = pack_chunk_bf16(x);
+                    if (c & 1) { if (valid) st_global_v8(orow + (c - 1) * 8, pend, pk); }
+                    else pend = pk;
+                }
+            };
+            const long long e0 = dbg ? clock64() : 0;
+            const int c_rot = a.v_transform ? c_se3 : D / 8;       // chunks below c_rot are stored as they are
+#pragma unroll 1
+            for (int c = 0; c < c_rot; ++c) {
+                float x[8];
+                next_o(c, x);
+                emit(c, x);
+            }
             long long e1 = 0, e2 = 0;
             if (a.v_transform) {
-                const int e_se3 = a.hd.triv, e_so3 = e_se3 + a.hd.se3, e_so2 = e_so3 + a.hd.so3;
-                if (a.hd.se3) {
+                if (c_so3 > c_se3) {
                     float M[16];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 q4 = __ldg(reinterpret_cast<const float4*>(a.se3_q + view * 16) + i);
                         M[4 * i] = q4.x; M[4 * i + 1] = q4.y; M[4 * i + 2] = q4.z; M[4 * i + 3] = q4.w;
                     }
-#pragma unroll
-                    for (int c = 0; c < D / 8; ++c)
-                        if (c * 8 >= e_se3 && c * 8 < e_so3) se3_apply(o + c * 8, M, tc);
+#pragma unroll 1
+                    for (int c = c_se3; c < c_so3; ++c) {
+                        float x[8];
+                        next_o(c, x);
+                        se3_apply(x, M, tc);
+                        emit(c, x);
+                    }
                 }
                 if (dbg) e1 = clock64();
-                if (a.hd.so3) {
+                if (c_so2 > c_so3) {
                     float W[34];
 #pragma unroll
                     for (int i = 0; i < 17; ++i) {
                         const float2 q2 = __ldg(reinterpret_cast<const float2*>(a.so3_q + view * 34) + i);
                         W[2 * i] = q2.x; W[2 * i + 1] = q2.y;
                     }
-#pragma unroll
-                    for (int c = 0; c < D / 8; ++c)
-                        if (c * 8 >= e_so3 && c * 8 < e_so2) so3_apply<true>(o + c * 8, W);
-                }
-                if (dbg) e2 = clock64();
-                if (a.hd.so2) {
-#pragma unroll
-                    for (int c = 0; c < D / 8; ++c) {
-                        if (c * 8 >= e_so2) {
-                            const So2Chunk sc = load_so2_chunk(so2, c, a.hd);
-                            const float cs8[8] = {sc.a.x, sc.a.y, sc.a.z, sc.a.w, sc.b.x, sc.b.y, sc.b.z, sc.b.w};
-                            so2_apply<true>(o + c * 8, cs8);
-                        }
+#pragma unroll 1
+                    for (int c = c_so3; c < c_so2; ++c) {
+                        float x[8];
+                        next_o(c, x);
+                        so3_apply<true>(x, W);
+                        emit(c, x);
                     }
                 }
-            }
-            if (valid) {
-                // 32-byte stores (STG.256): a thread owns a whole 2*D-byte output row, so every store instruction is one
-                // L2 sector per lane; pairing two 16-byte chunks halves the transaction count of the bf16 row.
-                TOut* orow = reinterpret_cast<TOut*>(a.out) + ((static_cast<int64_t>(ic.b) * a.Tq + tt) * a.H + ic.h) * D;
-                if (sizeof(TOut) == 4) {
-#pragma unroll
-                    for (int c = 0; c < D / 8; ++c)
-                        st_global_v8(orow + c * 8, make_uint4(oreg[c * 8], oreg[c * 8 + 1], oreg[c * 8 + 2], oreg[c * 8 + 3]),
-                                     make_uint4(oreg[c * 8 + 4], oreg[c * 8 + 5], oreg[c * 8 + 6], oreg[c * 8 + 7]));
-                } else {
-#pragma unroll
-                    for (int c = 0; c < D / 8; c += 2)
-                        st_global_v8(orow + c * 8, pack_chunk_bf16(o + c * 8), pack_chunk_bf16(o + c * 8 + 8));
+                if (dbg) e2 = clock64();
+                So2Chunk sc_cur = load_so2_chunk(so2, c_so2, a.hd);
+#pragma unroll 1
+                for (int c = c_so2; c < D / 8; ++c) {
+                    So2Chunk sc_nxt = sc_cur;
+                    if (c + 1 < D / 8) sc_nxt = load_so2_chunk(so2, c + 1, a.hd);
+                    float x[8];
+                    next_o(c, x);
+                    const float cs8[8] = {sc_cur.a.x, sc_cur.a.y, sc_cur.a.z, sc_cur.a.w, sc_cur.b.x, sc_cur.b.y, sc_cur.b.z, sc_cur.b.w};
+                    so2_apply<true>(x, cs8);
+                    emit(c, x);
+                    sc_cur = sc_nxt;
                 }
-                if (a.lse) a.lse[(static_cast<int64_t>(ic.b) * a.H + ic.h) * a.Tq + t] = m_used * a.scale + logf(l_run);
             }
+            tc_fence_before();
+            mbar_arrive(&bars[L::bOFree + X]);                  // O_X fully read: the next item's PV_X(0) may overwrite it
+            if (a.lse && valid)
+                a.lse[(static_cast<int64_t>(ic.b) * a.H + ic.h) * a.Tq + t] = m_used * a.scale + logf(l_run);
             if (dbg) {
                 const long long d_t3 = clock64();
                 d_loop += d_t1 - d_t0; d_wait_o += d_t2 - d_t1; d_epi += d_t3 - d_t2; ++d_items;

@@ -42,8 +42,9 @@ def main():
         print(f"  {nme:28s} per item {(d[:,i]/items).mean():8.0f} clk  ({100*(d[:,i]/d[:,0]).mean():5.1f}% of span)")
     print(f"  per key tile: loop {(d[:,1]/items/ntile).mean():.0f} clk, of which s_full wait {(d[:,3]/items/ntile).mean():.0f};"
           f" tensor work per tile-pair {2*2*128*128*cfg.head_dim*2/8192:.0f} clk")
-    for i, nme in ((6, "TMEM drain (one round trip) + o_free"), (7, "1/l + se3 pass"), (13, "so3 pass"), (14, "so2 pass + stores + lse")):
-        print(f"  epilogue part {nme:38s} per item {(d[:,i]/items).mean():7.0f} clk")
+    if True:
+        for i, nme in ((6, "setup (1/l, first tmem ld)"), (7, "triv+se3 chunks"), (13, "so3 chunks"), (14, "so2 chunks + o_free + lse")):
+            print(f"  epilogue part {nme:30s} per item {(d[:,i]/items).mean():7.0f} clk")
     for i, nme in ((8, "k_full"), (9, "v_full"), (10, "p_full"), (11, "o_free"), (12, "q_full")):
         print(f"  UMMA issuer wait on {nme:7s} per item {(d[:,i]/items).mean():8.0f} clk ({100*(d[:,i]/d[:,0]).mean():5.1f}% of span)")
 
