@@ -40,12 +40,19 @@ class GtaAttnParams(ctypes.Structure):
     )
 
 
+class GtaAttnBwdParams(ctypes.Structure):
+    _fields_ = [("fwd", GtaAttnParams), ("dout", c_void_p), ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
+                ("dtrans_coeff", c_void_p), ("workspace", c_void_p), ("workspace_bytes", c_size_t)]
+
+
 # every symbol include/gta_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "gta_attn_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gta_attn_fwd_workspace_bytes_ex": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "gta_attn_fwd_workspace_bytes_p": (c_size_t, [POINTER(GtaAttnParams)]),
     "gta_attn_fwd": (c_int, [POINTER(GtaAttnParams), c_void_p]),
+    "gta_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "gta_attn_bwd": (c_int, [POINTER(GtaAttnBwdParams), c_void_p]),
     "gta_rotate_debug": (c_int, [POINTER(GtaAttnParams), c_void_p, c_void_p, c_void_p, c_void_p]),
     "gta_build_reps": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_float, c_float, c_int, c_int] + [c_void_p] * 7),
     "gta_so2_mats": (c_int, [c_void_p, c_int64, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),

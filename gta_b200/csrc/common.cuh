@@ -23,6 +23,9 @@ int launch_wigner(const float* R, int64_t n, float* d1, float* d2, cudaStream_t 
 int launch_se3_inverse(const float* extr, int64_t n, float* inv, cudaStream_t st);
 int launch_t2_mats(const float* coord, int64_t n, float* mats, float* inv, cudaStream_t st);
 
+size_t attn_bwd_workspace_bytes(int B, int H, int Tq, int Tk, int D);
+int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st);
+
 // Generic path (gta_generic.cu): t2 block, euclid_sim, head layouts with blocks that are not multiples of 8.
 bool attn_needs_generic(const GtaAttnParams& p);
 size_t generic_workspace_bytes(const GtaAttnParams& p);

@@ -100,6 +100,15 @@ int gta_attn_fwd(const GtaAttnParams* p, void* stream) {
     return launch_attn_fwd(*p, st);
 }
 
+size_t gta_attn_bwd_workspace_bytes(int B, int H, int Tq, int Tk, int D) { return attn_bwd_workspace_bytes(B, H, Tq, Tk, D); }
+
+int gta_attn_bwd(const GtaAttnBwdParams* p, void* stream) {
+    if (!p) return set_error(GTA_ERR_INVALID, "null params");
+    int rc = validate_attn_params(&p->fwd);
+    if (rc) return rc;
+    return launch_attn_bwd(*p, static_cast<cudaStream_t>(stream));
+}
+
 int gta_rotate_debug(const GtaAttnParams* p, float* qt, float* kt, float* vt, void* stream) {
     int rc = validate_attn_params(p);
     if (rc) return rc;

@@ -1,0 +1,490 @@
+// Fused GTA attention BACKWARD for sm_100a: dQ, dK, dV and d(trans_coeff) of
+//
+//   O = rho_q^{-1} softmax((rho_q^{-T} Q)(rho_k K)^T * scale) (rho_k V)        (source/utils/gta.py:92-279)
+//
+// The block-diagonal reps are constant linear maps, so with Q' = rho_q^{-T} Q, K' = rho_k K, V' = rho_k V, O = rho_q^{-1} O':
+//   dO' = rho_q^{-T} dO (the same map the forward applies to Q)      delta = rowsum(dO * O) = rowsum(dO' * O')
+//   P = exp(Q'K'^T scale - lse),  dV' = P^T dO',  dP = dO' V'^T,  dS = P * (dP - delta) * scale,
+//   dQ' = dS K',  dK' = dS^T Q',        dQ = rho_q^{-1} dQ',  dK = rho_k^T dK',  dV = rho_k^T dV'.
+// scale_mask(trans_coeff) scales one column of the SE(3) matrices (gta.py:40-44), so d(trans_coeff) is a sum of
+// per-4-vector terms evaluated where the un-rotated gradients are still in registers.
+//
+// Launches: (1) staging — K'/V' tile images (gta_rotate_kv.cu), Q'/dO' tile images + delta (+ the output-side
+// trans_coeff term); (2) attn_bwd_dkv_kernel: one CTA per (b, h, 128-key tile) loops over the query tiles with
+// S^T = K'Q'^T and dP^T = V'dO'^T (SS MMAs), P^T / dS^T written back IN PLACE as bf16 and consumed from tensor memory by
+// dV' += P^T dO', dK' += dS^T Q' (TS MMAs, the operand tile images read MN-major); (3) attn_bwd_dq_kernel: one CTA per
+// (b, h, 128-query tile) loops over the key tiles with S, dP (SS) and dQ' += dS K' (TS).  Recomputing S and dP in both
+// kernels (7 instead of 5 MMAs per tile pair) avoids atomics on dQ and keeps every accumulator in tensor memory.
+// First version: correctness and tensor-core data flow; the MMA and SIMT phases of a tile are not overlapped yet.
+#include <cmath>
+
+#include "attn_common.cuh"
+
+namespace gta {
+
+struct BwdArgs {
+    const uint8_t* q_img; const uint8_t* do_img;     // [B*H*ntq] tile images of Q', dO'
+    const uint8_t* k_img; const uint8_t* v_img;      // [B*H*ntk] tile images of K', V'
+    const float* lse; const float* delta;            // [B,H,Tq]
+    void* dq; void* dk; void* dv;                    // [B,T,H,D] contiguous
+    const void* q; const void* k; const void* v;     // raw inputs (trans_coeff terms)
+    int64_t q_sb, q_sh, q_st, k_sb, k_sh, k_st, v_sb, v_sh, v_st;
+    float* dtc;
+    int B, H, Tq, Tk, Nq, Nk, tpvq, tpvk, ntq, ntk, C;
+    HeadDims hd;
+    const float* se3_q; const float* so3_q; const float* so2_q;
+    const float* se3_k; const float* so3_k; const float* so2_k;
+    const float* tc_ptr;
+    float scale, scale_log2;
+    int v_transform;
+};
+
+constexpr int kBwdThreads = 192;
+constexpr uint32_t kBwdTmemS = 0, kBwdTmemDP = 128, kBwdTmemAcc0 = 256, kBwdTmemAcc1 = 384;
+
+template <int D>
+struct BwdSmem {
+    static constexpr uint32_t kTile = 128u * D * 2u;
+    static constexpr uint32_t kFix0 = 0, kFix1 = kTile;          // the CTA's own two tiles (K',V' or Q',dO')
+    static constexpr uint32_t kStg0 = 2 * kTile;                  // [2 stages] streamed tile 0 (Q' / K')
+    static constexpr uint32_t kStg1 = 4 * kTile;                  // [2 stages] streamed tile 1 (dO' / V')
+    static constexpr uint32_t kLD = 6 * kTile;                    // float [2 buffers][2 (lse*log2e, delta)][128]
+    static constexpr uint32_t kBars = kLD + 2 * 2 * 128 * 4;
+    enum : int { bFix = 0, bFull = 1, bEmpty = 3, bSFull = 5, bPReady = 6, bDone = 7, bCount = 8 };
+    static constexpr uint32_t kTmemSlot = kBars + bCount * 8;
+    static constexpr uint32_t kUsed = kTmemSlot + 16;
+    static constexpr uint32_t kBytes = (kUsed + 1024 > 120u * 1024u) ? kUsed + 1024 : 120u * 1024u;
+};
+
+__device__ __forceinline__ void bwd_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Shared skeleton of the two kernels.  kDKV = true : fixed tiles K'_j, V'_j; streamed Q'_i, dO'_i; rows = keys.
+//                                      kDKV = false: fixed tiles Q'_i, dO'_i; streamed K'_j, V'_j; rows = queries.
+template <typename TIn, typename TOut, int D, bool kDKV>
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs a) {
+    using L = BwdSmem<D>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+    float* sLD = reinterpret_cast<float*>(smem + L::kLD);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
+
+    const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nstream = kDKV ? a.ntq : a.ntk;
+    const size_t bh = static_cast<size_t>(b) * a.H + h;
+    const uint8_t* fix0 = (kDKV ? a.k_img + (bh * a.ntk + tile) * L::kTile : a.q_img + (bh * a.ntq + tile) * L::kTile);
+    const uint8_t* fix1 = (kDKV ? a.v_img + (bh * a.ntk + tile) * L::kTile : a.do_img + (bh * a.ntq + tile) * L::kTile);
+    const uint8_t* stg0 = (kDKV ? a.q_img + bh * a.ntq * L::kTile : a.k_img + bh * a.ntk * L::kTile);
+    const uint8_t* stg1 = (kDKV ? a.do_img + bh * a.ntq * L::kTile : a.v_img + bh * a.ntk * L::kTile);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[L::bFix], 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&bars[L::bFull + s], 1); mbar_init(&bars[L::bEmpty + s], 1); }
+        mbar_init(&bars[L::bSFull], 1);
+        mbar_init(&bars[L::bPReady], 128);
+        mbar_init(&bars[L::bDone], 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+    if (warp < 4) {
+        // =========================================================== compute warpgroup: thread r <-> row r <-> TMEM lane r
+        const int r = threadIdx.x;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const float tc = a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f;
+        const float cs = a.scale_log2;
+        constexpr float kLog2e = 1.4426950408889634f;
+        const float* lse_bh = a.lse + bh * a.Tq;
+        const float* del_bh = a.delta + bh * a.Tq;
+        float my_lse2 = 0.f, my_del = 0.f;                   // dQ kernel: this row's statistics
+        if (!kDKV) {
+            const int t = tile * 128 + r;
+            if (t < a.Tq) { my_lse2 = lse_bh[t] * kLog2e; my_del = del_bh[t]; }
+        } else {                                             // dKV kernel: per-column statistics of query tile 0
+            const int t = r;
+            sLD[r] = t < a.Tq ? lse_bh[t] * kLog2e : 0.f;
+            sLD[128 + r] = t < a.Tq ? del_bh[t] : 0.f;
+            bwd_bar_sync(1);
+        }
+#pragma unroll 1
+        for (int i = 0; i < nstream; ++i) {
+            float nx_lse2 = 0.f, nx_del = 0.f;
+            if (kDKV && i + 1 < nstream) {                   // next query tile's statistics: loads in flight during this tile
+                const int t = (i + 1) * 128 + r;
+                if (t < a.Tq) { nx_lse2 = lse_bh[t] * kLog2e; nx_del = del_bh[t]; }
+            }
+            mbar_wait(&bars[L::bSFull], i & 1);
+            tc_fence_after();
+            const float* ld = sLD + (i & 1) * 256;
+            const int ncol = (kDKV ? a.Tq : a.Tk) - i * 128;           // valid streamed rows = valid columns of this tile
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t sr[32], dr[32];
+                tmem_ld32(lane_base + kBwdTmemS + c * 32, sr);
+                tmem_ld32(lane_base + kBwdTmemDP + c * 32, dr);
+                tmem_ld_wait();
+                uint32_t pp[16], ds[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    float pv[2], dv[2];
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const int col = c * 32 + 2 * u + w;
+                        const float l2 = kDKV ? ld[col] : my_lse2;
+                        const float dl = kDKV ? ld[128 + col] : my_del;
+                        float p = fast_exp2(fmaf(__uint_as_float(sr[2 * u + w]), cs, -l2));
+                        float d = p * (__uint_as_float(dr[2 * u + w]) - dl) * a.scale;
+                        if (col >= ncol) { p = 0.f; d = 0.f; }
+                        pv[w] = p; dv[w] = d;
+                    }
+                    pp[u] = pack_bf16x2(pv[0], pv[1]);
+                    ds[u] = pack_bf16x2(dv[0], dv[1]);
+                }
+                // in place: the packed columns of chunk c land behind the read pointer (columns 16c..16c+15)
+                if (kDKV) tmem_st16(lane_base + kBwdTmemS + c * 16, pp);
+                tmem_st16(lane_base + (kDKV ? kBwdTmemDP : kBwdTmemS) + c * 16, ds);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars[L::bPReady]);
+            if (kDKV && i + 1 < nstream) {
+                float* nd = sLD + ((i + 1) & 1) * 256;
+                nd[r] = nx_lse2; nd[128 + r] = nx_del;
+                bwd_bar_sync(1);
+            }
+        }
+
+        // ---- epilogue: accumulators -> registers (8 columns at a time) -> transposed / inverse rep -> global
+        mbar_wait(&bars[L::bDone], 0);
+        tc_fence_after();
+        const int T = kDKV ? a.Tk : a.Tq;
+        const int t = tile * 128 + r;
+        const bool valid = t < T;
+        const int tt = valid ? t : T - 1;
+        const size_t view = static_cast<size_t>(b) * (kDKV ? a.Nk : a.Nq) + tt / (kDKV ? a.tpvk : a.tpvq);
+        const float* se3 = (kDKV ? a.se3_k : a.se3_q) + view * 16;
+        const float* so3 = (kDKV ? a.so3_k : a.so3_q) + view * 34;
+        const float* so2 = (kDKV ? a.so2_k : a.so2_q) + (static_cast<size_t>(b) * T + tt) * a.C * 2;
+        const int64_t orow = ((static_cast<int64_t>(b) * T + tt) * a.H + h) * D;
+        const int c_se3 = a.hd.triv >> 3, c_so3 = c_se3 + (a.hd.se3 >> 3);
+        float dtc_part = 0.f;
+        constexpr int NACC = kDKV ? 2 : 1;
+#pragma unroll 1
+        for (int which = 0; which < NACC; ++which) {
+            // dKV kernel: which = 0 -> dV' (accumulator 0), which = 1 -> dK' (accumulator 1); dQ kernel: dQ' (accumulator 0)
+            const uint32_t acc = lane_base + (which == 0 ? kBwdTmemAcc0 : kBwdTmemAcc1);
+            TOut* dst = reinterpret_cast<TOut*>(kDKV ? (which == 0 ? a.dv : a.dk) : a.dq) + orow;
+            const bool rotate = kDKV ? (which == 1 || a.v_transform) : true;
+            const TIn* raw = kDKV
+                ? (which == 0 ? reinterpret_cast<const TIn*>(a.v) + b * a.v_sb + h * a.v_sh + static_cast<int64_t>(tt) * a.v_st
+                              : reinterpret_cast<const TIn*>(a.k) + b * a.k_sb + h * a.k_sh + static_cast<int64_t>(tt) * a.k_st)
+                : reinterpret_cast<const TIn*>(a.q) + b * a.q_sb + h * a.q_sh + static_cast<int64_t>(tt) * a.q_st;
+#pragma unroll 1
+            for (int c = 0; c < D / 8; ++c) {
+                uint32_t o8[8];
+                tmem_ld8(acc + c * 8, o8);
+                tmem_ld_wait();
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = __uint_as_float(o8[u]);
+                if (rotate && valid && a.dtc && c >= c_se3 && c < c_so3) {
+                    // d(trans_coeff): the un-rotated gradient times d(rep)/d(tc) applied to the raw input 4-vectors
+                    float M[16], xin[8];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 q4 = __ldg(reinterpret_cast<const float4*>(se3) + u);
+                        M[4 * u] = q4.x; M[4 * u + 1] = q4.y; M[4 * u + 2] = q4.z; M[4 * u + 3] = q4.w;
+                    }
+                    load_chunk<TIn>(raw + c * 8, xin);
+#pragma unroll
+                    for (int v4 = 0; v4 < 2; ++v4) {
+                        const float* g = x + 4 * v4;
+                        const float* y = xin + 4 * v4;
+                        if (kDKV) dtc_part += (g[0] * M[3] + g[1] * M[7] + g[2] * M[11]) * y[3];       // K', V': rows 0..2, column 3
+                        else dtc_part += g[3] * (M[3] * y[0] + M[7] * y[1] + M[11] * y[2]);              // Q': transposed rep
+                    }
+                }
+                if (rotate) {
+                    if (kDKV) apply_rep_chunk<kModeKVT>(x, c, a.hd, se3, so3, so2, tc);
+                    else apply_rep_chunk<kModeOut>(x, c, a.hd, se3, so3, so2, tc);
+                }
+                if (valid) store_chunk<TOut>(dst + c * 8, x);
+            }
+        }
+        if (a.dtc) {
+            dtc_part = warp_sum(dtc_part);
+            if (lane == 0 && dtc_part != 0.f) atomicAdd(a.dtc, dtc_part);
+        }
+    } else if (warp == 4) {
+        // =========================================================== UMMA issuer
+        constexpr uint32_t idesc_ss = make_idesc_bf16(128, 128, 0, 0);
+        constexpr uint32_t idesc_ts = make_idesc_bf16(128, D, 0, 1);
+        const uint32_t f0 = smem_u32(smem + L::kFix0), f1 = smem_u32(smem + L::kFix1);
+        mbar_wait(&bars[L::bFix], 0);
+#pragma unroll 1
+        for (int i = 0; i < nstream; ++i) {
+            const int s = i & 1;
+            const uint32_t g0 = smem_u32(smem + L::kStg0 + s * L::kTile), g1 = smem_u32(smem + L::kStg1 + s * L::kTile);
+            mbar_wait(&bars[L::bFull + s], (i >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                // dKV: S^T = K' Q'^T, dP^T = V' dO'^T   (A = fixed tile, B = streamed tile)
+                // dQ : S   = Q' K'^T, dP   = dO' V'^T   (A = fixed tile, B = streamed tile)
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ss(tmem_base + kBwdTmemS, desc_kmajor_sw64(f0, kk), desc_kmajor_sw64(g0, kk), idesc_ss, kk > 0);
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk)
+                    umma_ss(tmem_base + kBwdTmemDP, desc_kmajor_sw64(f1, kk), desc_kmajor_sw64(g1, kk), idesc_ss, kk > 0);
+                umma_commit(&bars[L::bSFull]);
+            }
+            __syncwarp();
+            mbar_wait(&bars[L::bPReady], i & 1);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t accf = (i > 0) ? 1u : 0u;
+                if (kDKV) {
+                    // dV' += P^T dO'   (A = P^T in TMEM, B = dO'_i read MN-major);  dK' += dS^T Q'
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + kk * 8, desc_mnmajor_sw64(g1, kk), idesc_ts,
+                                (kk > 0) ? 1u : accf);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_ts(tmem_base + kBwdTmemAcc1, tmem_base + kBwdTmemDP + kk * 8, desc_mnmajor_sw64(g0, kk), idesc_ts,
+                                (kk > 0) ? 1u : accf);
+                } else {
+                    // dQ' += dS K'     (A = dS in TMEM, B = K'_j read MN-major)
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + kk * 8, desc_mnmajor_sw64(g0, kk), idesc_ts,
+                                (kk > 0) ? 1u : accf);
+                }
+                umma_commit(&bars[L::bEmpty + s]);
+                if (i == nstream - 1) umma_commit(&bars[L::bDone]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================================================== bulk-copy producer
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars[L::bFix], 2 * L::kTile);
+            bulk_g2s(smem + L::kFix0, fix0, L::kTile, &bars[L::bFix]);
+            bulk_g2s(smem + L::kFix1, fix1, L::kTile, &bars[L::bFix]);
+        }
+#pragma unroll 1
+        for (int i = 0; i < nstream; ++i) {
+            const int s = i & 1;
+            if (i >= 2) mbar_wait(&bars[L::bEmpty + s], ((i >> 1) - 1) & 1);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&bars[L::bFull + s], 2 * L::kTile);
+                bulk_g2s(smem + L::kStg0 + s * L::kTile, stg0 + static_cast<size_t>(i) * L::kTile, L::kTile, &bars[L::bFull + s]);
+                bulk_g2s(smem + L::kStg1 + s * L::kTile, stg1 + static_cast<size_t>(i) * L::kTile, L::kTile, &bars[L::bFull + s]);
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- staging
+struct BwdStageArgs {
+    const void* x; int64_t sb, sh, st;     // rows [B,H,T,D] (strided)
+    uint8_t* img;                          // [B*H*ntiles] tile images
+    int B, H, T, D, N, tpv, ntiles, C;
+    HeadDims hd;
+    const float* se3; const float* so3; const float* so2; const float* tc_ptr;
+    int rotate;
+};
+
+// One thread per (row, 8-element chunk): raw row -> rho_q^{-T} -> bf16 operand tile image (zero rows past T).
+template <typename T>
+__global__ void bwd_stage_rows_kernel(const BwdStageArgs a) {
+    const int nch = a.D >> 3;
+    const int64_t total = static_cast<int64_t>(a.B) * a.H * a.ntiles * 128 * nch;
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = static_cast<int>(i % nch);
+    int64_t rr = i / nch;
+    const int row = static_cast<int>(rr % 128); rr /= 128;
+    const int tile = static_cast<int>(rr % a.ntiles); rr /= a.ntiles;
+    const int h = static_cast<int>(rr % a.H);
+    const int b = static_cast<int>(rr / a.H);
+    const int t = tile * 128 + row;
+    float x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = 0.f;
+    if (t < a.T) {
+        load_chunk<T>(reinterpret_cast<const T*>(a.x) + b * a.sb + h * a.sh + static_cast<int64_t>(t) * a.st + c * 8, x);
+        if (a.rotate) {
+            const size_t view = static_cast<size_t>(b) * a.N + t / a.tpv;
+            apply_rep_chunk<kModeQ>(x, c, a.hd, a.se3 + view * 16, a.so3 + view * 34,
+                                    a.so2 + (static_cast<size_t>(b) * a.T + t) * a.C * 2, a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f);
+        }
+    }
+    uint8_t* dst = a.img + ((static_cast<size_t>(b) * a.H + h) * a.ntiles + tile) * (static_cast<size_t>(128) * a.D * 2);
+    *reinterpret_cast<uint4*>(dst + tile_sw64_offset(row, c)) = pack_chunk_bf16(x);
+}
+
+// delta[b,h,t] = sum_d dO * O, and the output-side trans_coeff term: O_i = sum_j M_ij O'_j + tc * M_i3 * O'_3 (i < 3),
+// O_3 = M_33 O'_3 with M = E_q  =>  d/dtc = sum_{i<3} dO_i M_i3 O_3 / M_33 per SE(3) 4-vector.  One thread per row.
+template <typename T>
+__global__ void bwd_delta_kernel(const T* __restrict__ out, const T* __restrict__ dout, float* __restrict__ delta,
+                                 float* dtc, const float* __restrict__ se3_q, int B, int Tq, int H, int D, int Nq, int tpvq,
+                                 int triv, int se3, int v_transform) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t total = static_cast<int64_t>(B) * Tq * H;
+    float part = 0.f;
+    if (i < total) {
+        const int h = static_cast<int>(i % H);
+        const int64_t bt = i / H;
+        const int t = static_cast<int>(bt % Tq), b = static_cast<int>(bt / Tq);
+        const T* o = out + i * D;
+        const T* g = dout + i * D;
+        const float* M = se3_q + (static_cast<size_t>(b) * Nq + t / tpvq) * 16;
+        float acc = 0.f;
+        for (int c = 0; c < D / 8; ++c) {
+            float xo[8], xg[8];
+            load_chunk<T>(o + c * 8, xo);
+            load_chunk<T>(g + c * 8, xg);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fmaf(xo[u], xg[u], acc);
+            if (dtc && v_transform && se3 && c * 8 >= triv && c * 8 < triv + se3) {
+#pragma unroll
+                for (int v4 = 0; v4 < 2; ++v4)
+                    part += (xg[4 * v4] * M[3] + xg[4 * v4 + 1] * M[7] + xg[4 * v4 + 2] * M[11]) * xo[4 * v4 + 3] / M[15];
+            }
+        }
+        delta[(static_cast<int64_t>(b) * H + h) * Tq + t] = acc;
+    }
+    if (dtc) {
+        part = warp_sum(part);
+        if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(dtc, part);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- host side
+static size_t bwd_align(size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); }
+
+size_t attn_bwd_workspace_bytes(int B, int H, int Tq, int Tk, int D) {
+    if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || D <= 0) return 0;
+    const size_t tile = kv_tile_bytes(D);
+    const size_t ntq = num_kv_tiles(Tq), ntk = num_kv_tiles(Tk);
+    return 2 * bwd_align(static_cast<size_t>(B) * H * ntq * tile) + bwd_align(2 * static_cast<size_t>(B) * H * ntk * tile) +
+           bwd_align(static_cast<size_t>(B) * H * Tq * 4);
+}
+
+template <typename TIn, typename TOut, int D>
+static int launch_bwd_d(const BwdArgs& a, cudaStream_t st) {
+    using L = BwdSmem<D>;
+    auto kkv = attn_bwd_kernel<TIn, TOut, D, true>;
+    auto kq = attn_bwd_kernel<TIn, TOut, D, false>;
+    cudaError_t e = cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::kBytes));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::kBytes));
+    if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    kkv<<<dim3(a.ntk, a.H, a.B), kBwdThreads, L::kBytes, st>>>(a);
+    kq<<<dim3(a.ntq, a.H, a.B), kBwdThreads, L::kBytes, st>>>(a);
+    return check_launch("gta_attn_bwd");
+}
+
+template <typename T>
+static int launch_bwd_t(const BwdArgs& a, int D, cudaStream_t st) {
+    switch (D) {
+        case 32: return launch_bwd_d<T, T, 32>(a, st);
+        case 64: return launch_bwd_d<T, T, 64>(a, st);
+        case 96: return launch_bwd_d<T, T, 96>(a, st);
+        case 128: return launch_bwd_d<T, T, 128>(a, st);
+    }
+    return set_error(GTA_ERR_UNSUPPORTED, "head dim %d", D);
+}
+
+int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st) {
+    const GtaAttnParams& p = bp.fwd;
+    if (attn_needs_generic(p))
+        return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_bwd: the t2 / euclid_sim / unaligned-block configurations have no fused backward");
+    if (p.out_dtype != p.in_dtype) return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_bwd: out/dout must have the dtype of q/k/v");
+    if (!p.lse || !bp.dout || !bp.dq || !bp.dk || !bp.dv) return set_error(GTA_ERR_INVALID, "gta_attn_bwd: null lse/dout/dq/dk/dv");
+    const size_t need = attn_bwd_workspace_bytes(p.B, p.H, p.Tq, p.Tk, p.D);
+    if (!bp.workspace || bp.workspace_bytes < need) return set_error(GTA_ERR_INVALID, "gta_attn_bwd: workspace too small (need %zu bytes)", need);
+    if (reinterpret_cast<uintptr_t>(bp.workspace) & 1023) return set_error(GTA_ERR_INVALID, "gta_attn_bwd: workspace must be 1024-byte aligned");
+
+    const size_t tile = kv_tile_bytes(p.D);
+    const int ntq = num_kv_tiles(p.Tq), ntk = num_kv_tiles(p.Tk);
+    uint8_t* ws = static_cast<uint8_t*>(bp.workspace);
+    uint8_t* q_img = ws;
+    uint8_t* do_img = q_img + bwd_align(static_cast<size_t>(p.B) * p.H * ntq * tile);
+    uint8_t* kv_img = do_img + bwd_align(static_cast<size_t>(p.B) * p.H * ntq * tile);
+    float* delta = reinterpret_cast<float*>(kv_img + bwd_align(2 * static_cast<size_t>(p.B) * p.H * ntk * tile));
+
+    // K'/V' tile images: the forward's staging kernel on plain bf16 images
+    GtaAttnParams kvp = p;
+    kvp.workspace = kv_img;
+    kvp.workspace_bytes = 2 * static_cast<size_t>(p.B) * p.H * ntk * tile;
+    kvp.flags = GTA_FLAG_FAST_FP32;
+    int rc = launch_rotate_kv(kvp, st);
+    if (rc) return rc;
+
+    const bool bf = p.in_dtype == GTA_DTYPE_BF16;
+    BwdStageArgs sa;
+    sa.B = p.B; sa.H = p.H; sa.T = p.Tq; sa.D = p.D; sa.N = p.Nq; sa.tpv = p.Tq / p.Nq; sa.ntiles = ntq; sa.C = p.so2 >> 1;
+    sa.hd = HeadDims{p.triv, p.se3, p.so3, p.so2};
+    sa.se3 = p.reps.se3_q; sa.so3 = p.reps.so3_q; sa.so2 = p.reps.so2_q; sa.tc_ptr = p.trans_coeff;
+    const int64_t total = static_cast<int64_t>(p.B) * p.H * ntq * 128 * (p.D >> 3);
+    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+    sa.x = p.q; sa.sb = p.q_stride_b; sa.sh = p.q_stride_h; sa.st = p.q_stride_t; sa.img = q_img; sa.rotate = 1;
+    if (bf) bwd_stage_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(sa); else bwd_stage_rows_kernel<float><<<blocks, 256, 0, st>>>(sa);
+    // dO' = rho_q^{-T} dO: dout is [B,Tq,H,D] contiguous
+    sa.x = bp.dout; sa.sb = static_cast<int64_t>(p.Tq) * p.H * p.D; sa.sh = p.D; sa.st = static_cast<int64_t>(p.H) * p.D;
+    sa.img = do_img; sa.rotate = p.v_transform;
+    if (bf) bwd_stage_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(sa); else bwd_stage_rows_kernel<float><<<blocks, 256, 0, st>>>(sa);
+    {
+        const int64_t rows = static_cast<int64_t>(p.B) * p.Tq * p.H;
+        const unsigned nb = static_cast<unsigned>((rows + 127) / 128);
+        float* dtc = p.se3 ? bp.dtrans_coeff : nullptr;
+        if (bf) bwd_delta_kernel<__nv_bfloat16><<<nb, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(p.out), static_cast<const __nv_bfloat16*>(bp.dout),
+                                                                    delta, dtc, p.reps.se3_q, p.B, p.Tq, p.H, p.D, p.Nq, p.Tq / p.Nq, p.triv, p.se3, p.v_transform);
+        else bwd_delta_kernel<float><<<nb, 128, 0, st>>>(static_cast<const float*>(p.out), static_cast<const float*>(bp.dout), delta, dtc,
+                                                         p.reps.se3_q, p.B, p.Tq, p.H, p.D, p.Nq, p.Tq / p.Nq, p.triv, p.se3, p.v_transform);
+    }
+    rc = check_launch("gta_attn_bwd (staging)");
+    if (rc) return rc;
+
+    BwdArgs a;
+    a.q_img = q_img; a.do_img = do_img; a.k_img = kv_img; a.v_img = kv_img + static_cast<size_t>(p.B) * p.H * ntk * tile;
+    a.lse = p.lse; a.delta = delta;
+    a.dq = bp.dq; a.dk = bp.dk; a.dv = bp.dv;
+    a.q = p.q; a.k = p.k; a.v = p.v;
+    a.q_sb = p.q_stride_b; a.q_sh = p.q_stride_h; a.q_st = p.q_stride_t;
+    a.k_sb = p.k_stride_b; a.k_sh = p.k_stride_h; a.k_st = p.k_stride_t;
+    a.v_sb = p.v_stride_b; a.v_sh = p.v_stride_h; a.v_st = p.v_stride_t;
+    a.dtc = p.se3 ? bp.dtrans_coeff : nullptr;
+    a.B = p.B; a.H = p.H; a.Tq = p.Tq; a.Tk = p.Tk; a.Nq = p.Nq; a.Nk = p.Nk; a.tpvq = p.Tq / p.Nq; a.tpvk = p.Tk / p.Nk;
+    a.ntq = ntq; a.ntk = ntk; a.C = p.so2 >> 1;
+    a.hd = HeadDims{p.triv, p.se3, p.so3, p.so2};
+    a.se3_q = p.reps.se3_q; a.so3_q = p.reps.so3_q; a.so2_q = p.reps.so2_q;
+    a.se3_k = p.reps.se3_k; a.so3_k = p.reps.so3_k; a.so2_k = p.reps.so2_k;
+    a.tc_ptr = p.trans_coeff;
+    a.scale = p.scale; a.scale_log2 = p.scale * 1.4426950408889634f;
+    a.v_transform = p.v_transform;
+    return bf ? launch_bwd_t<__nv_bfloat16>(a, p.D, st) : launch_bwd_t<float>(a, p.D, st);
+}
+
+}  // namespace gta

@@ -15,6 +15,7 @@ enum RepMode : int {
     kModeQ = 0,    // rho_q^{-T}: (E_q*msk)^T, D_q, R(th_q)
     kModeKV = 1,   // rho_k:      inv(E_k)*msk, D_k, R(th_k)
     kModeOut = 2,  // rho_q^{-1}: E_q*msk, D_q^T, R(th_q)^T
+    kModeKVT = 3,  // rho_k^T:    (inv(E_k)*msk)^T, D_k^T, R(th_k)^T   (backward: dK = rho_k^T dK', dV = rho_k^T dV')
 };
 
 struct HeadDims {
@@ -95,7 +96,7 @@ __device__ __forceinline__ void apply_rep_chunk(float* x, int c, const HeadDims&
             float4 r = __ldg(reinterpret_cast<const float4*>(se3m) + i);
             M[4 * i] = r.x; M[4 * i + 1] = r.y; M[4 * i + 2] = r.z; M[4 * i + 3] = r.w;
         }
-        if (kMode == kModeQ) se3_apply_T(x, M, tc); else se3_apply(x, M, tc);
+        if (kMode == kModeQ || kMode == kModeKVT) se3_apply_T(x, M, tc); else se3_apply(x, M, tc);
         return;
     }
     if (e < hd.triv + hd.se3 + hd.so3) {
@@ -105,7 +106,7 @@ __device__ __forceinline__ void apply_rep_chunk(float* x, int c, const HeadDims&
             float2 r = __ldg(reinterpret_cast<const float2*>(so3m) + i);
             W[2 * i] = r.x; W[2 * i + 1] = r.y;
         }
-        if (kMode == kModeOut) so3_apply<true>(x, W); else so3_apply<false>(x, W);
+        if (kMode == kModeOut || kMode == kModeKVT) so3_apply<true>(x, W); else so3_apply<false>(x, W);
         return;
     }
     {
@@ -115,7 +116,7 @@ __device__ __forceinline__ void apply_rep_chunk(float* x, int c, const HeadDims&
         float4 r1 = __ldg(reinterpret_cast<const float4*>(so2cs + 2 * pc) + 1);
         cs[0] = r0.x; cs[1] = r0.y; cs[2] = r0.z; cs[3] = r0.w;
         cs[4] = r1.x; cs[5] = r1.y; cs[6] = r1.z; cs[7] = r1.w;
-        if (kMode == kModeOut) so2_apply<true>(x, cs); else so2_apply<false>(x, cs);
+        if (kMode == kModeOut || kMode == kModeKVT) so2_apply<true>(x, cs); else so2_apply<false>(x, cs);
     }
 }
 

@@ -6,9 +6,10 @@ Same names, argument meaning and return convention as the reference so that it d
     import gta_b200.gta as fast
     fast.install()        # rebinds source.layers.multihead_geometric_transform_attention (+ source.utils.gta)
 
-Forward only (inference / no_grad).  Every f_dims layout and flag of the reference function is served by the CUDA
+Forward and backward: under autograd the op is a torch.autograd.Function whose backward is the library's fused
+gta_attn_bwd (gradients for q, k, v and trans_coeff).  Every f_dims layout and flag of the reference function is served by the CUDA
 library (the `t2` block, `euclid_sim` and layouts with blocks that are not multiples of 8 through its generic path).
-Calls that need autograd or a CPU tensor are delegated to the original reference function when it was captured by
+Calls that need autograd through the generic path or a CPU tensor are delegated to the original reference function when it was captured by
 install(), and raise NotImplementedError otherwise — there is no silent CPU or PyTorch fallback inside this package.
 """
 from __future__ import annotations
@@ -95,6 +96,34 @@ def _delegate(reason, *args, **kwargs):
     return _original(*args, **kwargs)
 
 
+class _FusedGtaAttention(torch.autograd.Function):
+    """Differentiable wrapper: forward = gta_attn_fwd (+ log-sum-exp), backward = gta_attn_bwd.  Gradients flow to q, k, v
+    and to the layer's trans_coeff parameter (source/layers.py:188-191); the rep tensors are constants, as in the
+    reference (SO(3) reps are detached at gta.py:194-197, the SE(3) / SO(2) / coordinates come from the batch)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, trans_coeff, packed, f_dims, scale, v_transform):
+        tc = None if trans_coeff is None else trans_coeff.detach()
+        out, lse = ops.gta_attention_fwd(q, k, v, packed, f_dims, trans_coeff=tc, scale=scale, v_transform=v_transform,
+                                         return_lse=True)
+        ctx.save_for_backward(q, k, v, out, lse, tc if tc is not None else q.new_empty(0))
+        ctx.packed, ctx.f_dims, ctx.scale, ctx.v_transform = packed, f_dims, scale, v_transform
+        ctx.has_tc = tc is not None
+        ctx.tc_shape = None if trans_coeff is None else trans_coeff.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse, tc = ctx.saved_tensors
+        dq, dk, dv, dtc = ops.gta_attention_bwd(dout, q, k, v, out, lse, ctx.packed, ctx.f_dims,
+                                                trans_coeff=tc if ctx.has_tc else None, scale=ctx.scale,
+                                                v_transform=ctx.v_transform)
+        gtc = None
+        if ctx.has_tc and ctx.needs_input_grad[3] and dtc is not None:
+            gtc = dtc.reshape(ctx.tc_shape).to(tc.dtype)
+        return dq, dk, dv, gtc, None, None, None, None
+
+
 def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, trans_coeff=1.0, v_transform=True,
                                             euclid=False, **kwargs):
     """Drop-in for source/utils/gta.py:92-279.  q [B,H,Tq,C], k,v [B,H,Tk,C] (strided views are consumed
@@ -106,8 +135,10 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
         return _delegate("a non-CUDA tensor", *args, **kw)
     if q.dtype not in (torch.bfloat16, torch.float32) or k.dtype != q.dtype or v.dtype != q.dtype:
         return _delegate("dtype %s" % q.dtype, *args, **kw)
-    if torch.is_grad_enabled() and any(t.requires_grad for t in (q, k, v)):
-        return _delegate("autograd (the fused backward is not implemented yet)", *args, **kw)
+    needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in (q, k, v)) or
+                                              (torch.is_tensor(trans_coeff) and trans_coeff.requires_grad))
+    if needs_grad and (euclid or g("t2") or any(g(n) % 8 for n in ("triv", "se3", "so3", "so2"))):
+        return _delegate("autograd through the t2 / euclid_sim / unaligned-block path", *args, **kw)
     B, H, Tq, D = q.shape
     packed = _pack_reps(reps, f_dims, B, euclid)
     if g("so3") and not g("se3"):
@@ -121,6 +152,9 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
     tc = None
     if g("se3"):
         tc = trans_coeff if torch.is_tensor(trans_coeff) else torch.tensor([float(trans_coeff)], device=q.device)
+    if needs_grad:
+        tc_param = tc if (tc is not None and torch.is_tensor(trans_coeff)) else tc
+        return _FusedGtaAttention.apply(q, k, v, tc_param, packed, dict(f_dims), scale, bool(v_transform)), None
     out = ops.gta_attention_fwd(q, k, v, packed, f_dims, trans_coeff=tc, scale=scale, v_transform=v_transform,
                                 euclid=euclid)
     return out, None

@@ -8,7 +8,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from ._lib import GtaAttnParams, GtaReps, check, lib
+from ._lib import GtaAttnBwdParams, GtaAttnParams, GtaReps, check, lib
 
 
 def _stream() -> int:
@@ -145,6 +145,37 @@ def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: P
     check(lib().gta_attn_fwd(p, _stream()), "gta_attn_fwd")
     res = out.permute(0, 2, 1, 3)
     return (res, lse) if return_lse else res
+
+
+def gta_attention_bwd(dout: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor,
+                      lse: torch.Tensor, reps: PackedReps, f_dims: dict, *, trans_coeff: Optional[torch.Tensor] = None,
+                      scale: Optional[float] = None, v_transform: bool = True):
+    """Backward of gta_attention_fwd.  `out` is the forward result ([B,H,Tq,D] view of a [B,Tq,H,D] buffer), `lse` its
+    log-sum-exp, `dout` the gradient w.r.t. `out` (any layout).  Returns (dq, dk, dv, dtrans_coeff) with dq/dk/dv shaped
+    like q/k/v (views of contiguous [B,T,H,D] buffers) and dtrans_coeff a [1] fp32 tensor (None without an se3 block)."""
+    B, H, Tq, D = q.shape
+    Tk = k.shape[2]
+    dev = q.device
+    if scale is None:
+        scale = D ** -0.5
+    if trans_coeff is not None:
+        trans_coeff = trans_coeff.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
+    o_c = out.permute(0, 2, 1, 3).contiguous()                    # [B,Tq,H,D] (no copy for the forward's own buffer)
+    do_c = dout.to(o_c.dtype).permute(0, 2, 1, 3).contiguous()
+    dq = torch.empty(B, Tq, H, D, device=dev, dtype=q.dtype)
+    dk = torch.empty(B, Tk, H, D, device=dev, dtype=q.dtype)
+    dv = torch.empty(B, Tk, H, D, device=dev, dtype=q.dtype)
+    has_se3 = bool(int(f_dims.get("se3", 0) or 0))
+    dtc = torch.zeros(1, device=dev, dtype=torch.float32) if has_se3 else None
+    bp = GtaAttnBwdParams()
+    bp.fwd = _params(q, k, v, o_c, reps, f_dims, trans_coeff, scale, v_transform, 0, lse.contiguous())
+    bp.dout, bp.dq, bp.dk, bp.dv, bp.dtrans_coeff = _ptr(do_c), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dtc)
+    nbytes = lib().gta_attn_bwd_workspace_bytes(B, H, Tq, Tk, D)
+    ws = _workspace(dev, nbytes)
+    bp.workspace = (ws.data_ptr() + 1023) // 1024 * 1024
+    bp.workspace_bytes = nbytes
+    check(lib().gta_attn_bwd(bp, _stream()), "gta_attn_bwd")
+    return dq.permute(0, 2, 1, 3), dk.permute(0, 2, 1, 3), dv.permute(0, 2, 1, 3), dtc
 
 
 def rotate_debug(q, k, v, reps: PackedReps, f_dims: dict, *, trans_coeff=None, v_transform=True, euclid=False):

@@ -114,6 +114,30 @@ size_t gta_attn_fwd_workspace_bytes_p(const GtaAttnParams* p);
 /* Fused forward: O = rho_q^{-1} softmax((rho_q^{-T} Q)(rho_k K)^T * scale) (rho_k V). */
 int gta_attn_fwd(const GtaAttnParams* p, void* stream);
 
+/* Backward of gta_attn_fwd (what torch.autograd derives from source/utils/gta.py:92-279 + source/layers.py:207-211 in
+ * the reference's training step, source/trainer.py:69-83): gradients w.r.t. q, k, v and the layer's trans_coeff
+ * (source/layers.py:188-191; the SO(3) reps are detached, gta.py:194-197, the SO(2)/SE(3) matrices are data).
+ *   fwd          the forward call's parameters: q/k/v (+strides), dims, reps, trans_coeff, scale, dtypes, v_transform;
+ *                fwd.out = the forward OUTPUT [B,Tq,H,D] and fwd.lse = its log-sum-exp [B,H,Tq] (both required);
+ *                fwd.workspace / flags are ignored.  Fused-path configurations only (no t2 / euclid).
+ *   dout         [B,Tq,H,D] contiguous, dtype of out (= dtype of q/k/v)
+ *   dq, dk, dv   [B,Tq,H,D] / [B,Tk,H,D] contiguous, dtype of q/k/v (written)
+ *   dtrans_coeff optional device scalar, ACCUMULATED into (atomicAdd; zero it first)
+ * Tensor-core math is bf16 with fp32 accumulation for both input dtypes. */
+typedef struct GtaAttnBwdParams {
+    GtaAttnParams fwd;
+    const void* dout;
+    void* dq;
+    void* dk;
+    void* dv;
+    float* dtrans_coeff;
+    void* workspace;          /* >= gta_attn_bwd_workspace_bytes(...), 1024-byte aligned */
+    size_t workspace_bytes;
+} GtaAttnBwdParams;
+
+size_t gta_attn_bwd_workspace_bytes(int B, int H, int Tq, int Tk, int D);
+int gta_attn_bwd(const GtaAttnBwdParams* p, void* stream);
+
 /* Rotated operands only (q' = rho_q^{-T} q etc.), fp32 [B,H,T,D] contiguous; testing / inspection. */
 int gta_rotate_debug(const GtaAttnParams* p, float* qt, float* kt, float* vt, void* stream);
 

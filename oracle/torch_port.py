@@ -107,9 +107,9 @@ def build_reps(cfg, extr_q, extr_k, coord_q, coord_k) -> Dict[str, torch.Tensor]
 def _scale_translation(M: torch.Tensor, tc) -> torch.Tensor:
     """M * scale_mask(tc): the translation column (rows 0..2 of column 3) is multiplied by tc
     (gta.py:40-44,140-141)."""
-    M = M.clone()
-    M[..., :3, 3] = M[..., :3, 3] * tc
-    return M
+    one = torch.tensor([[1.0, 1.0, 1.0, 0.0]] * 3 + [[0.0, 0.0, 0.0, 1.0]], dtype=M.dtype, device=M.device)
+    col = torch.tensor([[0.0, 0.0, 0.0, 1.0]] * 3 + [[0.0, 0.0, 0.0, 0.0]], dtype=M.dtype, device=M.device)
+    return M * (one + col * tc)        # out of place: differentiable in tc (a learnable parameter, layers.py:188-191)
 
 
 def _per_view(x: torch.Tensor, N: int) -> torch.Tensor:

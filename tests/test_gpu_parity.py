@@ -392,3 +392,83 @@ def test_generic_rotated_operands_match_oracle():
         q2, k2, v2 = tp.transform_qkv(cfg, inp["q"], inp["k"], inp["v"], r, 0.3)
         for a, b in ((qt, q2), (kt, k2), (vt, v2)):
             assert (a.cpu() - b).abs().max() < 5e-6
+
+
+# ------------------------------------------------------------------------------------------------ backward (f1)
+def _grad_oracle(cfg, inp, tc, dout):
+    """Gradients of the torch restatement (fp64 autograd) — pinned to the reference's autograd by
+    tests/test_oracle.py::test_grad_oracle_matches_reference_autograd."""
+    from oracle import torch_port as tp
+    q, k, v = (inp[n].double().clone().requires_grad_(True) for n in "qkv")
+    tcv = torch.tensor([tc], dtype=torch.float64, requires_grad=True)
+    d = lambda t: t.double()
+    out = tp.gta_attention(cfg, q, k, v, d(inp["extr_q"]), d(inp["extr_k"]), d(inp["coord_q"]), d(inp["coord_k"]),
+                           trans_coeff=tcv)
+    out.backward(dout.double())
+    g = lambda t: None if t is None else t.float().numpy()
+    return out.detach().float().numpy(), g(q.grad), g(k.grad), g(v.grad), g(tcv.grad)
+
+
+@pytest.mark.parametrize("case", [
+    (CFG1_B, 2, 2, 16, 16, False, 2, torch.bfloat16, 0.3, True),        # one partial tile, D = 32
+    (MSN_SO3, 3, 2, 40, 64, True, 2, torch.bfloat16, 0.3, True),        # cross, ragged tiles, D = 96
+    (MSN_SO3, 5, 5, 256, 256, False, 1, torch.bfloat16, 0.01, True),    # MSN encoder shape
+    (CLEVR, 3, 2, 171, 300, True, 1, torch.bfloat16, 0.5, True),        # D = 64, views straddle tiles, Tq = 513
+    (CLEVR, 2, 2, 150, 150, False, 1, torch.bfloat16, 0.5, False),      # v_transform = False
+    (MSN_SO3, 3, 2, 40, 64, True, 1, torch.float32, 0.3, True),         # fp32 I/O (bf16 tensor-core math in the backward)
+], ids=["cfg1b", "msn_cross", "msn_enc", "clevr_dec", "clevr_novt", "msn_cross_f32"])
+def test_fused_backward_matches_autograd_oracle(case):
+    """dq, dk, dv and d(trans_coeff) of the fused backward, through the public drop-in under autograd, against fp64
+    autograd of the oracle on the same (rounded) inputs.  bf16 tensor-core math: errors relative to the gradient scale."""
+    from gta_b200 import gta as fast
+    from oracle import torch_port as tp
+    base, nq, nk, tq, tk, cross, B, dtype, tc, vt = case
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk, v_transform=vt)
+    inp = make_inputs(cfg, B, tq, tk, cross=cross, seed=41, dtype=dtype)
+    gen = torch.Generator().manual_seed(7)
+    dout = torch.randn(inp["q"].shape, generator=gen).to(dtype)
+    ref_out, rq, rk, rv, rtc = _grad_oracle(cfg, inp, tc, dout.float())
+
+    r = tp.build_reps(cfg, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"])
+    extras = {"se3rep_q": torch.linalg.inv(inp["extr_q"]).cuda(), "se3rep_k": r["se3_k"].cuda(),
+              "inv_se3rep_q": r["se3_qinv"].cuda()}
+    if cfg.so3:
+        extras.update({"so3rep_q": [r["so3_d1_q"].cuda(), r["so3_d2_q"].cuda()],
+                       "so3rep_k": [r["so3_d1_k"].cuda(), r["so3_d2_k"].cuda()]})
+    extras.update({"so2rep_q": tp.so2_mats(r["so2_th_q"]).cuda(), "so2rep_k": tp.so2_mats(r["so2_th_k"]).cuda()})
+
+    class AttnFn:
+        scale = cfg.head_dim ** -0.5
+    q, k, v = (inp[n].cuda().clone().requires_grad_(True) for n in "qkv")
+    tcp = torch.nn.Parameter(torch.tensor([tc], device="cuda"))
+    out, _ = fast.multihead_geometric_transform_attention(q, k, v, AttnFn(), cfg.f_dims, extras, trans_coeff=tcp,
+                                                          v_transform=vt)
+    assert out.requires_grad
+    out.backward(dout.cuda())
+    torch.cuda.synchronize()
+    assert np.abs(out.detach().float().cpu().numpy() - ref_out).max() < _tol(ref_out, tc)
+    for name, got, ref in (("dq", q.grad, rq), ("dk", k.grad, rk), ("dv", v.grad, rv)):
+        got = got.float().cpu().numpy()
+        assert np.isfinite(got).all(), name
+        err, scale_ = np.abs(got - ref).max(), np.abs(ref).max()
+        assert err < 2e-2 * scale_ + 1e-3, (name, err, scale_)
+    got_tc = float(tcp.grad.float().cpu())
+    assert abs(got_tc - float(rtc[0])) < 3e-2 * max(1.0, abs(float(rtc[0]))), (got_tc, float(rtc[0]))
+
+
+def test_backward_abi_direct_and_linearity():
+    """ops.gta_attention_bwd called directly: gradients are linear in dout, and dtrans_coeff is accumulated per call."""
+    ops = _ops()
+    cfg = GtaConfig(**MSN_SO3, n_q_views=2, n_k_views=2)
+    inp = make_inputs(cfg, 1, 100, 100, cross=False, seed=43, dtype=torch.bfloat16)
+    reps = _dev_reps(cfg, inp)
+    q, k, v = (inp[n].cuda() for n in "qkv")
+    tc = torch.tensor([0.2], device="cuda")
+    out, lse = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True)
+    dout = torch.randn(out.shape, device="cuda").bfloat16()
+    g1 = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc)
+    g2 = ops.gta_attention_bwd(dout * 2, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc)
+    for a, b in zip(g1[:3], g2[:3]):
+        assert a.shape == q.shape
+        assert (2 * a.float() - b.float()).abs().max() <= 2e-2 * b.float().abs().max()
+    assert abs(2 * float(g1[3]) - float(g2[3])) <= 2e-2 * abs(float(g2[3])) + 1e-4

@@ -173,3 +173,29 @@ def test_ablation_blocks_against_live_reference(base, nq, nk, tq, tk, cross, vt)
     assert (o2 - ref).abs().max() < 2e-6
     if cfg.t2_dim():
         assert (tp.t2_mats(inp["coord_k"]) - ex["t2rep_k"]).abs().max() == 0
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("base,nq,nk,tq,tk,cross", [(MSN_SO3, 3, 2, 8, 16, True), (CLEVR, 2, 2, 21, 21, False)])
+def test_grad_oracle_matches_reference_autograd(base, nq, nk, tq, tk, cross):
+    """The gradient checker of the GPU tests (autograd through oracle/torch_port.py) against autograd through the
+    UNMODIFIED reference function: dq, dk, dv and d(trans_coeff)."""
+    cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
+    inp = make_inputs(cfg, 2, tq, tk, cross=cross, seed=23)
+    dout = torch.randn(inp["q"].shape, generator=torch.Generator().manual_seed(1))
+    grads = []
+    for impl in ("ref", "port"):
+        q, k, v = (inp[n].clone().requires_grad_(True) for n in "qkv")
+        tc = torch.tensor([0.3], requires_grad=True)
+        if impl == "ref":
+            m = ref_harness.load()
+            extras = ref_harness.ref_reps(cfg, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"], cross)
+            out, _ = m.gta.multihead_geometric_transform_attention(
+                q, k, v, attn_fn=ref_harness._AttnFn(cfg.head_dim ** -0.5), f_dims=dict(cfg.f_dims), reps=extras,
+                trans_coeff=tc, v_transform=True, euclid=False)
+        else:
+            out = tp.gta_attention(cfg, q, k, v, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"], trans_coeff=tc)
+        out.backward(dout)
+        grads.append((q.grad, k.grad, v.grad, tc.grad))
+    for a, b in zip(*grads):
+        assert (a - b).abs().max() < 5e-6 * max(1.0, float(b.abs().max()))
