@@ -216,6 +216,7 @@ def main():
     ap.add_argument("--flags", type=int, default=0, help="GTA_FLAG_* bits for gta_attn_fwd (1 = P in TMEM)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--backward", action="store_true", help="also time the fused backward (adds a `backward` object)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -358,6 +359,18 @@ def main():
         e2e = {"value": world * B * nq * tq / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e, "steps": n_e2e}
 
+    bwd = None
+    if args.backward:
+        out_f, lse_f = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True)
+        dout = torch.randn(out_f.shape, device=dev).to(out_f.dtype)
+        bwd_fn = lambda: ops.gta_attention_bwd(dout, q, k, v, out_f, lse_f, reps, cfg.f_dims, trans_coeff=tc)
+        for _ in range(3):
+            bwd_fn()
+        ms_bwd = timed(bwd_fn, args.steps)
+        bwd = {"ms": ms_bwd, "kernels": "K'/V'/Q'/dO' staging + delta + attn_bwd_kernel<dKV> + attn_bwd_kernel<dQ>",
+               "tflops_algorithmic": 2.5 * 4.0 * B * H * nq * tq * nk * tk * D / (ms_bwd * 1e-3) / 1e12,
+               "fwd_bwd_Mtokens_per_s": world * B * nq * tq / ((ms_step + ms_bwd) * 1e-3) / 1e6}
+
     if rank == 0:
         Tq, Tk = nq * tq, nk * tk
         flops = 4.0 * B * H * Tq * Tk * D
@@ -375,7 +388,7 @@ def main():
                            p_operand="tmem" if args.flags & 1 else "smem"),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic_bytes(args.workload, B),
-                         "kernel": "attn_fwd3_kernel", "kernel_ms": ms_attn, "stage_kernel_ms": ms_stage,
+                         "kernel": "attn_fwd3_kernel (persistent two-tile pipeline)", "kernel_ms": ms_attn, "stage_kernel_ms": ms_stage,
                          "flops_per_launch": flops, "peak_source": pk_src +
                          (" burst" if total_s < 2.0 else " sustained")},
             "gpu_launches": launches_per_step * args.steps,
@@ -383,6 +396,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if bwd:
+            line["backward"] = bwd
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline(cfg, wl)
         print(json.dumps(line), flush=True)
