@@ -39,7 +39,7 @@ struct BwdArgs {
     int v_transform;
 };
 
-constexpr int kBwdThreads = 192;
+constexpr int kBwdThreads = 320;
 constexpr uint32_t kBwdTmemS = 0, kBwdTmemDP = 128, kBwdTmemAcc0 = 256, kBwdTmemAcc1 = 384;
 
 template <int D>
@@ -48,7 +48,7 @@ struct BwdSmem {
     static constexpr uint32_t kFix0 = 0, kFix1 = kTile;          // the CTA's own two tiles (K',V' or Q',dO')
     static constexpr uint32_t kStg0 = 2 * kTile;                  // [2 stages] streamed tile 0 (Q' / K')
     static constexpr uint32_t kStg1 = 4 * kTile;                  // [2 stages] streamed tile 1 (dO' / V')
-    static constexpr uint32_t kLD = 6 * kTile;                    // float [2 buffers][2 (lse*log2e, delta)][128]
+    static constexpr uint32_t kLD = 6 * kTile;                    // float [2 warpgroups][2 buffers][lse*log2e 64 | delta 64]
     static constexpr uint32_t kBars = kLD + 2 * 2 * 128 * 4;
     enum : int { bFix = 0, bFull = 1, bEmpty = 3, bSFull = 5, bPReady = 6, bDone = 7, bCount = 8 };
     static constexpr uint32_t kTmemSlot = kBars + bCount * 8;
@@ -57,6 +57,9 @@ struct BwdSmem {
 };
 
 __device__ __forceinline__ void bwd_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// TMEM column of the packed bf16 A operand for K-step kk (16 rows of the streamed tile): the first compute warpgroup packs
+// columns 0..63 into 0..31, the second 64..127 into 64..95.
+__device__ __forceinline__ constexpr uint32_t pk_off(int kk) { return kk < 4 ? kk * 8u : 64u + (kk - 4) * 8u; }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -87,11 +90,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         mbar_init(&bars[L::bFix], 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&bars[L::bFull + s], 1); mbar_init(&bars[L::bEmpty + s], 1); }
         mbar_init(&bars[L::bSFull], 1);
-        mbar_init(&bars[L::bPReady], 128);
+        mbar_init(&bars[L::bPReady], 256);
         mbar_init(&bars[L::bDone], 1);
         fence_mbar_init();
     }
-    if (warp == 4) {
+    if (warp == 8) {
         tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
     }
@@ -100,70 +103,74 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    if (warp < 4) {
-        // =========================================================== compute warpgroup: thread r <-> row r <-> TMEM lane r
-        const int r = threadIdx.x;
-        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    if (warp < 8) {
+        // =========================================================== two compute warpgroups: thread r <-> row r <-> TMEM
+        // lane r in both; warpgroup w owns columns [64w, 64w+64) of every S / dP tile (no exchange is needed: lse and
+        // delta are known), which halves the latency of the SIMT phase between the two MMA phases of a tile.
+        const int wgc = warp >> 2;
+        const int r = threadIdx.x & 127;
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         const float tc = a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f;
         const float cs = a.scale_log2;
         constexpr float kLog2e = 1.4426950408889634f;
         const float* lse_bh = a.lse + bh * a.Tq;
         const float* del_bh = a.delta + bh * a.Tq;
         float my_lse2 = 0.f, my_del = 0.f;                   // dQ kernel: this row's statistics
+        // dKV kernel: per-column statistics of this warpgroup's 64 query columns, [buffer][lse*log2e 64 | delta 64]
+        float* sLDw = sLD + wgc * 256;
+        auto col_stat = [&](int i) {                         // thread r fetches one of the 128 values of query tile i
+            const int t = i * 128 + wgc * 64 + (r & 63);
+            if (t >= a.Tq) return 0.f;
+            return r < 64 ? lse_bh[t] * kLog2e : del_bh[t];
+        };
         if (!kDKV) {
             const int t = tile * 128 + r;
             if (t < a.Tq) { my_lse2 = lse_bh[t] * kLog2e; my_del = del_bh[t]; }
-        } else {                                             // dKV kernel: per-column statistics of query tile 0
-            const int t = r;
-            sLD[r] = t < a.Tq ? lse_bh[t] * kLog2e : 0.f;
-            sLD[128 + r] = t < a.Tq ? del_bh[t] : 0.f;
-            bwd_bar_sync(1);
+        } else {
+            sLDw[r] = col_stat(0);
+            bwd_bar_sync(1 + wgc);
         }
+        // packed results go to the first 32 columns of the warpgroup's OWN 64-column range (columns 0..31 / 64..95):
+        // never into columns the other warpgroup still has to read
+        const uint32_t pk_col = wgc * 64;
 #pragma unroll 1
         for (int i = 0; i < nstream; ++i) {
-            float nx_lse2 = 0.f, nx_del = 0.f;
-            if (kDKV && i + 1 < nstream) {                   // next query tile's statistics: loads in flight during this tile
-                const int t = (i + 1) * 128 + r;
-                if (t < a.Tq) { nx_lse2 = lse_bh[t] * kLog2e; nx_del = del_bh[t]; }
-            }
+            float nx_stat = 0.f;
+            if (kDKV && i + 1 < nstream) nx_stat = col_stat(i + 1);   // in flight during this tile
             mbar_wait(&bars[L::bSFull], i & 1);
             tc_fence_after();
-            const float* ld = sLD + (i & 1) * 256;
-            const int ncol = (kDKV ? a.Tq : a.Tk) - i * 128;           // valid streamed rows = valid columns of this tile
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t sr[32], dr[32];
-                tmem_ld32(lane_base + kBwdTmemS + c * 32, sr);
-                tmem_ld32(lane_base + kBwdTmemDP + c * 32, dr);
-                tmem_ld_wait();
-                uint32_t pp[16], ds[16];
+            const float* ld = sLDw + (i & 1) * 128;
+            const int ncol = (kDKV ? a.Tq : a.Tk) - i * 128 - wgc * 64;   // valid columns of this warpgroup's half
+            uint32_t sr[64], dr[64];
+            tmem_ld32(lane_base + kBwdTmemS + wgc * 64, sr);
+            tmem_ld32(lane_base + kBwdTmemS + wgc * 64 + 32, sr + 32);
+            tmem_ld32(lane_base + kBwdTmemDP + wgc * 64, dr);
+            tmem_ld32(lane_base + kBwdTmemDP + wgc * 64 + 32, dr + 32);
+            tmem_ld_wait();
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    float pv[2], dv[2];
+            for (int u = 0; u < 32; ++u) {
+                float pv[2], dv[2];
 #pragma unroll
-                    for (int w = 0; w < 2; ++w) {
-                        const int col = c * 32 + 2 * u + w;
-                        const float l2 = kDKV ? ld[col] : my_lse2;
-                        const float dl = kDKV ? ld[128 + col] : my_del;
-                        float p = fast_exp2(fmaf(__uint_as_float(sr[2 * u + w]), cs, -l2));
-                        float d = p * (__uint_as_float(dr[2 * u + w]) - dl) * a.scale;
-                        if (col >= ncol) { p = 0.f; d = 0.f; }
-                        pv[w] = p; dv[w] = d;
-                    }
-                    pp[u] = pack_bf16x2(pv[0], pv[1]);
-                    ds[u] = pack_bf16x2(dv[0], dv[1]);
+                for (int w = 0; w < 2; ++w) {
+                    const int col = 2 * u + w;
+                    const float l2 = kDKV ? ld[col] : my_lse2;
+                    const float dl = kDKV ? ld[64 + col] : my_del;
+                    float p = fast_exp2(fmaf(__uint_as_float(sr[col]), cs, -l2));
+                    float d = p * (__uint_as_float(dr[col]) - dl) * a.scale;
+                    if (col >= ncol) { p = 0.f; d = 0.f; }
+                    pv[w] = p; dv[w] = d;
                 }
-                // in place: the packed columns of chunk c land behind the read pointer (columns 16c..16c+15)
-                if (kDKV) tmem_st16(lane_base + kBwdTmemS + c * 16, pp);
-                tmem_st16(lane_base + (kDKV ? kBwdTmemDP : kBwdTmemS) + c * 16, ds);
+                sr[u] = pack_bf16x2(pv[0], pv[1]);           // in place: pair u lands in slot u <= 2u
+                dr[u] = pack_bf16x2(dv[0], dv[1]);
             }
+            if (kDKV) tmem_st32(lane_base + kBwdTmemS + pk_col, sr);
+            tmem_st32(lane_base + (kDKV ? kBwdTmemDP : kBwdTmemS) + pk_col, dr);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars[L::bPReady]);
             if (kDKV && i + 1 < nstream) {
-                float* nd = sLD + ((i + 1) & 1) * 256;
-                nd[r] = nx_lse2; nd[128 + r] = nx_del;
-                bwd_bar_sync(1);
+                sLDw[((i + 1) & 1) * 128 + r] = nx_stat;
+                bwd_bar_sync(1 + wgc);
             }
         }
 
@@ -181,10 +188,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         const int64_t orow = ((static_cast<int64_t>(b) * T + tt) * a.H + h) * D;
         const int c_se3 = a.hd.triv >> 3, c_so3 = c_se3 + (a.hd.se3 >> 3);
         float dtc_part = 0.f;
-        constexpr int NACC = kDKV ? 2 : 1;
-#pragma unroll 1
-        for (int which = 0; which < NACC; ++which) {
-            // dKV kernel: which = 0 -> dV' (accumulator 0), which = 1 -> dK' (accumulator 1); dQ kernel: dQ' (accumulator 0)
+        // dKV kernel: warpgroup 0 finishes dV' (accumulator 0), warpgroup 1 dK' (accumulator 1);
+        // dQ kernel: the two warpgroups split the columns of dQ' (accumulator 0).
+        const int c_lo = kDKV ? 0 : wgc * (D / 16), c_hi = kDKV ? D / 8 : (wgc + 1) * (D / 16);
+        {
+            const int which = kDKV ? wgc : 0;
             const uint32_t acc = lane_base + (which == 0 ? kBwdTmemAcc0 : kBwdTmemAcc1);
             TOut* dst = reinterpret_cast<TOut*>(kDKV ? (which == 0 ? a.dv : a.dk) : a.dq) + orow;
             const bool rotate = kDKV ? (which == 1 || a.v_transform) : true;
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                               : reinterpret_cast<const TIn*>(a.k) + b * a.k_sb + h * a.k_sh + static_cast<int64_t>(tt) * a.k_st)
                 : reinterpret_cast<const TIn*>(a.q) + b * a.q_sb + h * a.q_sh + static_cast<int64_t>(tt) * a.q_st;
 #pragma unroll 1
-            for (int c = 0; c < D / 8; ++c) {
+            for (int c = c_lo; c < c_hi; ++c) {
                 uint32_t o8[8];
                 tmem_ld8(acc + c * 8, o8);
                 tmem_ld_wait();
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
             dtc_part = warp_sum(dtc_part);
             if (lane == 0 && dtc_part != 0.f) atomicAdd(a.dtc, dtc_part);
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // =========================================================== UMMA issuer
         constexpr uint32_t idesc_ss = make_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_ts = make_idesc_bf16(128, D, 0, 1);
@@ -260,17 +268,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                     // dV' += P^T dO'   (A = P^T in TMEM, B = dO'_i read MN-major);  dK' += dS^T Q'
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
-                        umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + kk * 8, desc_mnmajor_sw64(g1, kk), idesc_ts,
+                        umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + pk_off(kk), desc_mnmajor_sw64(g1, kk), idesc_ts,
                                 (kk > 0) ? 1u : accf);
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
-                        umma_ts(tmem_base + kBwdTmemAcc1, tmem_base + kBwdTmemDP + kk * 8, desc_mnmajor_sw64(g0, kk), idesc_ts,
+                        umma_ts(tmem_base + kBwdTmemAcc1, tmem_base + kBwdTmemDP + pk_off(kk), desc_mnmajor_sw64(g0, kk), idesc_ts,
                                 (kk > 0) ? 1u : accf);
                 } else {
                     // dQ' += dS K'     (A = dS in TMEM, B = K'_j read MN-major)
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
-                        umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + kk * 8, desc_mnmajor_sw64(g0, kk), idesc_ts,
+                        umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + pk_off(kk), desc_mnmajor_sw64(g0, kk), idesc_ts,
                                 (kk > 0) ? 1u : accf);
                 }
                 umma_commit(&bars[L::bEmpty + s]);
@@ -299,7 +307,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
