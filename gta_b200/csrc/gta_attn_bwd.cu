@@ -37,6 +37,7 @@ struct BwdArgs {
     const float* tc_ptr;
     float scale, scale_log2;
     int v_transform;
+    long long* dbg;      // optional [2 kernels][num CTAs][16] clock64 phase sums (tools/bwd_phase_timing.py)
 };
 
 constexpr int kBwdThreads = 320;
@@ -133,12 +134,42 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         // packed results go to the first 32 columns of the warpgroup's OWN 64-column range (columns 0..31 / 64..95):
         // never into columns the other warpgroup still has to read
         const uint32_t pk_col = wgc * 64;
+        const size_t cta = (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        long long* dbg = (a.dbg && threadIdx.x == 0) ? a.dbg + ((kDKV ? 0 : static_cast<size_t>(gridDim.x) * gridDim.y * gridDim.z) + cta) * 16 : nullptr;
+        long long d_wait = 0, d_ld = 0, d_cmp = 0, d_st = 0;
+        const long long d_start = dbg ? clock64() : 0;
 #pragma unroll 1
         for (int i = 0; i < nstream; ++i) {
             float nx_stat = 0.f;
             if (kDKV && i + 1 < nstream) nx_stat = col_stat(i + 1);   // in flight during this tile
+            if (i == nstream - 1) {
+                // pull this row's epilogue operands (view matrices, SO(2) table) into L1 while the last tile is computed
+                const int T_ = kDKV ? a.Tk : a.Tq;
+                const int tt_ = min(tile * 128 + r, T_ - 1);
+                const size_t view_ = static_cast<size_t>(b) * (kDKV ? a.Nk : a.Nq) + tt_ / (kDKV ? a.tpvk : a.tpvq);
+                if (a.hd.se3) prefetch_l1((kDKV ? a.se3_k : a.se3_q) + view_ * 16);
+                if (a.hd.so3) {
+                    prefetch_l1((kDKV ? a.so3_k : a.so3_q) + view_ * 34);
+                    prefetch_l1((kDKV ? a.so3_k : a.so3_q) + view_ * 34 + 32);
+                }
+                if (a.hd.so2) {
+                    const float* so2_ = (kDKV ? a.so2_k : a.so2_q) + (static_cast<size_t>(b) * T_ + tt_) * a.C * 2;
+                    for (int off = 0; off < a.C * 2; off += 32) prefetch_l1(so2_ + off);
+                }
+                if (a.dtc && a.hd.se3) {                     // ... and the raw se3 elements the trans_coeff term reads
+                    const TIn* raw_ = kDKV
+                        ? (wgc == 0 ? reinterpret_cast<const TIn*>(a.v) + b * a.v_sb + h * a.v_sh + static_cast<int64_t>(tt_) * a.v_st
+                                    : reinterpret_cast<const TIn*>(a.k) + b * a.k_sb + h * a.k_sh + static_cast<int64_t>(tt_) * a.k_st)
+                        : reinterpret_cast<const TIn*>(a.q) + b * a.q_sb + h * a.q_sh + static_cast<int64_t>(tt_) * a.q_st;
+                    for (int e = a.hd.triv; e < a.hd.triv + a.hd.se3; e += 128 / static_cast<int>(sizeof(TIn)))
+                        prefetch_l1(raw_ + e);
+                    prefetch_l1(raw_ + a.hd.triv + a.hd.se3 - 1);
+                }
+            }
+            const long long d0 = dbg ? clock64() : 0;
             mbar_wait(&bars[L::bSFull], i & 1);
             tc_fence_after();
+            const long long d1 = dbg ? clock64() : 0;
             const float* ld = sLDw + (i & 1) * 128;
             const int ncol = (kDKV ? a.Tq : a.Tk) - i * 128 - wgc * 64;   // valid columns of this warpgroup's half
             uint32_t sr[64], dr[64];
@@ -147,27 +178,48 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
             tmem_ld32(lane_base + kBwdTmemDP + wgc * 64, dr);
             tmem_ld32(lane_base + kBwdTmemDP + wgc * 64 + 32, dr + 32);
             tmem_ld_wait();
+            const long long d2 = dbg ? clock64() : 0;
+            // dS = P * (dP - delta) * scale = P * (dP*scale - delta*scale): one FFMA + one FMUL per element
+            const float my_dls = my_del * a.scale;
 #pragma unroll
-            for (int u = 0; u < 32; ++u) {
-                float pv[2], dv[2];
+            for (int u4 = 0; u4 < 16; ++u4) {                // 4 columns per step (one 16-byte read of each statistic)
+                float l2[4], dls[4];
+                if (kDKV) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(ld + 4 * u4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(ld + 64 + 4 * u4);
+                    l2[0] = a4.x; l2[1] = a4.y; l2[2] = a4.z; l2[3] = a4.w;
+                    dls[0] = b4.x * a.scale; dls[1] = b4.y * a.scale; dls[2] = b4.z * a.scale; dls[3] = b4.w * a.scale;
+                } else {
 #pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                    const int col = 2 * u + w;
-                    const float l2 = kDKV ? ld[col] : my_lse2;
-                    const float dl = kDKV ? ld[64 + col] : my_del;
-                    float p = fast_exp2(fmaf(__uint_as_float(sr[col]), cs, -l2));
-                    float d = p * (__uint_as_float(dr[col]) - dl) * a.scale;
-                    if (col >= ncol) { p = 0.f; d = 0.f; }
-                    pv[w] = p; dv[w] = d;
+                    for (int w = 0; w < 4; ++w) { l2[w] = my_lse2; dls[w] = my_dls; }
                 }
-                sr[u] = pack_bf16x2(pv[0], pv[1]);           // in place: pair u lands in slot u <= 2u
-                dr[u] = pack_bf16x2(dv[0], dv[1]);
+                float pv[4], dv[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int col = 4 * u4 + w;
+                    pv[w] = fast_exp2(fmaf(__uint_as_float(sr[col]), cs, -l2[w]));
+                    dv[w] = pv[w] * fmaf(__uint_as_float(dr[col]), a.scale, -dls[w]);
+                }
+                // in place: pairs (4u4, 4u4+1), (4u4+2, 4u4+3) land in slots 2u4, 2u4+1 <= the columns just consumed
+                sr[2 * u4] = pack_bf16x2(pv[0], pv[1]); sr[2 * u4 + 1] = pack_bf16x2(pv[2], pv[3]);
+                dr[2 * u4] = pack_bf16x2(dv[0], dv[1]); dr[2 * u4 + 1] = pack_bf16x2(dv[2], dv[3]);
             }
+            if (ncol < 64) {                                 // ragged last tile: zero the packed columns past the end
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    if (2 * u + 1 >= ncol) {
+                        const uint32_t keep = (2 * u < ncol) ? 0x0000FFFFu : 0u;
+                        sr[u] &= keep; dr[u] &= keep;
+                    }
+                }
+            }
+            const long long d3 = dbg ? clock64() : 0;
             if (kDKV) tmem_st32(lane_base + kBwdTmemS + pk_col, sr);
             tmem_st32(lane_base + (kDKV ? kBwdTmemDP : kBwdTmemS) + pk_col, dr);
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars[L::bPReady]);
+            if (dbg) { const long long d4 = clock64(); d_wait += d1 - d0; d_ld += d2 - d1; d_cmp += d3 - d2; d_st += d4 - d3; }
             if (kDKV && i + 1 < nstream) {
                 sLDw[((i + 1) & 1) * 128 + r] = nx_stat;
                 bwd_bar_sync(1 + wgc);
@@ -175,8 +227,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         }
 
         // ---- epilogue: accumulators -> registers (8 columns at a time) -> transposed / inverse rep -> global
+        const long long d_loop_end = dbg ? clock64() : 0;
         mbar_wait(&bars[L::bDone], 0);
         tc_fence_after();
+        const long long d_done = dbg ? clock64() : 0;
         const int T = kDKV ? a.Tk : a.Tq;
         const int t = tile * 128 + r;
         const bool valid = t < T;
@@ -185,7 +239,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         const float* se3 = (kDKV ? a.se3_k : a.se3_q) + view * 16;
         const float* so3 = (kDKV ? a.so3_k : a.so3_q) + view * 34;
         const float* so2 = (kDKV ? a.so2_k : a.so2_q) + (static_cast<size_t>(b) * T + tt) * a.C * 2;
-        const int64_t orow = ((static_cast<int64_t>(b) * T + tt) * a.H + h) * D;
         const int c_se3 = a.hd.triv >> 3, c_so3 = c_se3 + (a.hd.se3 >> 3);
         float dtc_part = 0.f;
         // dKV kernel: warpgroup 0 finishes dV' (accumulator 0), warpgroup 1 dK' (accumulator 1);
@@ -194,29 +247,51 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         {
             const int which = kDKV ? wgc : 0;
             const uint32_t acc = lane_base + (which == 0 ? kBwdTmemAcc0 : kBwdTmemAcc1);
-            TOut* dst = reinterpret_cast<TOut*>(kDKV ? (which == 0 ? a.dv : a.dk) : a.dq) + orow;
             const bool rotate = kDKV ? (which == 1 || a.v_transform) : true;
             const TIn* raw = kDKV
                 ? (which == 0 ? reinterpret_cast<const TIn*>(a.v) + b * a.v_sb + h * a.v_sh + static_cast<int64_t>(tt) * a.v_st
                               : reinterpret_cast<const TIn*>(a.k) + b * a.k_sb + h * a.k_sh + static_cast<int64_t>(tt) * a.k_st)
                 : reinterpret_cast<const TIn*>(a.q) + b * a.q_sb + h * a.q_sh + static_cast<int64_t>(tt) * a.q_st;
+            constexpr uint32_t kPitch = D * sizeof(TOut) + (sizeof(TOut) == 2 ? 16 : 0);   // +16: conflict-free 16-byte row writes
+            uint8_t* stage_base = smem + ((kDKV && which == 1) ? L::kStg1 : L::kStg0);
+            uint8_t* stage_row = stage_base + static_cast<size_t>(r) * kPitch;
+            const bool want_tc = rotate && valid && a.dtc != nullptr && a.hd.se3 > 0;
+            // the row's view matrices once, in registers (the 128 score registers of the main loop are dead here): one
+            // L2 round trip per row instead of one per chunk
+            ViewReps vr;
+            if (rotate || want_tc) load_view_reps(vr, a.hd, se3, so3);
+            const float* M = vr.M;
+            // one chunk ahead: the accumulator columns (tcgen05.ld is asynchronous until wait::ld) and, for the
+            // trans_coeff term, the raw input chunk (a global load whose latency would otherwise be paid per chunk)
+            uint32_t o8[8];
+            constexpr int kAhead = 4;                        // raw chunks in flight: a global round trip is ~3 iterations
+            RawChunk<TIn> ring[kAhead];
+            auto want_raw = [&](int c) { return want_tc && c >= c_se3 && c < c_so3 && c < c_hi; };
+#pragma unroll
+            for (int u = 0; u < kAhead; ++u) {
+                zero_raw(ring[u]);
+                if (want_raw(c_lo + u)) load_raw(raw + (c_lo + u) * 8, ring[u]);
+            }
+            tmem_ld8(acc + c_lo * 8, o8);
+            long long e_wait = 0, e_cmp = 0;
 #pragma unroll 1
             for (int c = c_lo; c < c_hi; ++c) {
-                uint32_t o8[8];
-                tmem_ld8(acc + c * 8, o8);
+                const long long t0_ = dbg ? clock64() : 0;
                 tmem_ld_wait();
+                const long long t1_ = dbg ? clock64() : 0;
                 float x[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) x[u] = __uint_as_float(o8[u]);
-                if (rotate && valid && a.dtc && c >= c_se3 && c < c_so3) {
-                    // d(trans_coeff): the un-rotated gradient times d(rep)/d(tc) applied to the raw input 4-vectors
-                    float M[16], xin[8];
+                const RawChunk<TIn> raw_cur = ring[0];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float4 q4 = __ldg(reinterpret_cast<const float4*>(se3) + u);
-                        M[4 * u] = q4.x; M[4 * u + 1] = q4.y; M[4 * u + 2] = q4.z; M[4 * u + 3] = q4.w;
-                    }
-                    load_chunk<TIn>(raw + c * 8, xin);
+                for (int u = 0; u + 1 < kAhead; ++u) ring[u] = ring[u + 1];
+                if (want_raw(c + kAhead)) load_raw(raw + (c + kAhead) * 8, ring[kAhead - 1]);
+                const So2Chunk sc = rotate ? load_so2_chunk(so2, c, a.hd) : So2Chunk{};
+                if (c + 1 < c_hi) tmem_ld8(acc + (c + 1) * 8, o8);
+                if (want_tc && c >= c_se3 && c < c_so3) {
+                    // d(trans_coeff): the un-rotated gradient times d(rep)/d(tc) applied to the raw input 4-vectors
+                    float xin[8];
+                    raw_to_f32(raw_cur, xin);
 #pragma unroll
                     for (int v4 = 0; v4 < 2; ++v4) {
                         const float* g = x + 4 * v4;
@@ -226,15 +301,39 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                     }
                 }
                 if (rotate) {
-                    if (kDKV) apply_rep_chunk<kModeKVT>(x, c, a.hd, se3, so3, so2, tc);
-                    else apply_rep_chunk<kModeOut>(x, c, a.hd, se3, so3, so2, tc);
+                    if (kDKV) apply_rep_chunk_pre<kModeKVT>(x, c, a.hd, vr, sc, tc);
+                    else apply_rep_chunk_pre<kModeOut>(x, c, a.hd, vr, sc, tc);
                 }
-                if (valid) store_chunk<TOut>(dst + c * 8, x);
+                // rows are staged in shared memory (the streamed-tile buffers are idle now) and written out below with
+                // consecutive threads on consecutive 16-byte pieces of a row: a thread-per-row store is one 16-byte
+                // transaction per lane and instruction, which made this epilogue 25 % of the kernel.
+                store_chunk<TOut>(reinterpret_cast<TOut*>(stage_row) + c * 8, x);
+                if (dbg) { e_wait += t1_ - t0_; e_cmp += clock64() - t1_; }
             }
+            const long long t2_ = dbg ? clock64() : 0;
+            // hand the staged rows to the cooperative store
+            if (kDKV) asm volatile("bar.sync %0, 128;" ::"r"(3 + wgc) : "memory");
+            else asm volatile("bar.sync 3, 256;" ::: "memory");
+            constexpr int kPieces = D * static_cast<int>(sizeof(TOut)) / 16;      // 16-byte pieces per row
+            const int nthr = kDKV ? 128 : 256, tid = kDKV ? r : static_cast<int>(threadIdx.x);
+            const int nrows = min(128, T - tile * 128);
+            TOut* gbase = reinterpret_cast<TOut*>(kDKV ? (which == 0 ? a.dv : a.dk) : a.dq);
+            for (int idx = tid; idx < nrows * kPieces; idx += nthr) {
+                const int row = idx / kPieces, pc = idx - row * kPieces;
+                const uint4 val = *reinterpret_cast<const uint4*>(stage_base + static_cast<size_t>(row) * kPitch + pc * 16);
+                TOut* grow = gbase + ((static_cast<int64_t>(b) * T + tile * 128 + row) * a.H + h) * D;
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(grow) + pc * 16) = val;
+            }
+            if (dbg) { dbg[8] = e_wait; dbg[9] = e_cmp; dbg[10] = clock64() - t2_; dbg[11] = t2_ - d_done; }
         }
         if (a.dtc) {
             dtc_part = warp_sum(dtc_part);
             if (lane == 0 && dtc_part != 0.f) atomicAdd(a.dtc, dtc_part);
+        }
+        if (dbg) {
+            const long long d_end = clock64();
+            dbg[0] = d_end - d_start; dbg[1] = d_wait; dbg[2] = d_ld; dbg[3] = d_cmp; dbg[4] = d_st;
+            dbg[5] = d_end - d_loop_end; dbg[6] = nstream; dbg[7] = d_done - d_loop_end;
         }
     } else if (warp == 8) {
         // =========================================================== UMMA issuer
@@ -492,6 +591,7 @@ int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st) {
     a.tc_ptr = p.trans_coeff;
     a.scale = p.scale; a.scale_log2 = p.scale * 1.4426950408889634f;
     a.v_transform = p.v_transform;
+    a.dbg = p.debug_clocks;
     return bf ? launch_bwd_t<__nv_bfloat16>(a, p.D, st) : launch_bwd_t<float>(a, p.D, st);
 }
 

@@ -197,15 +197,15 @@ __device__ __forceinline__ void apply_rep_chunk_pre(float* x, int c, const HeadD
     const int e = c * 8;
     if (e < hd.triv) return;
     if (e < hd.triv + hd.se3) {
-        if (kMode == kModeQ) se3_apply_T(x, vr.M, tc); else se3_apply(x, vr.M, tc);
+        if (kMode == kModeQ || kMode == kModeKVT) se3_apply_T(x, vr.M, tc); else se3_apply(x, vr.M, tc);
         return;
     }
     if (e < hd.triv + hd.se3 + hd.so3) {
-        if (kMode == kModeOut) so3_apply<true>(x, vr.W); else so3_apply<false>(x, vr.W);
+        if (kMode == kModeOut || kMode == kModeKVT) so3_apply<true>(x, vr.W); else so3_apply<false>(x, vr.W);
         return;
     }
     const float cs[8] = {sc.a.x, sc.a.y, sc.a.z, sc.a.w, sc.b.x, sc.b.y, sc.b.z, sc.b.w};
-    if (kMode == kModeOut) so2_apply<true>(x, cs); else so2_apply<false>(x, cs);
+    if (kMode == kModeOut || kMode == kModeKVT) so2_apply<true>(x, cs); else so2_apply<false>(x, cs);
 }
 
 // Raw (unconverted) chunk loads so that several can be in flight before the first conversion.
