@@ -15,7 +15,11 @@
 // dV' += P^T dO', dK' += dS^T Q' (TS MMAs, the operand tile images read MN-major); (3) attn_bwd_dq_kernel: one CTA per
 // (b, h, 128-query tile) loops over the key tiles with S, dP (SS) and dQ' += dS K' (TS).  Recomputing S and dP in both
 // kernels (7 instead of 5 MMAs per tile pair) avoids atomics on dQ and keeps every accumulator in tensor memory.
-// First version: correctness and tensor-core data flow; the MMA and SIMT phases of a tile are not overlapped yet.
+// Head dims <= 96 pass P / dS through shared memory (K-major operand tiles) so that the next tile's S / dP MMAs overlap
+// the SIMT phase of the current one; kNW compute warpgroups split the columns of every S / dP tile.  Measured (B200, MSN
+// shape, tools/bwd_phase_timing.py): the SIMT phase (~2.2 k clk per tile in the dK/dV kernel) and the per-CTA epilogue
+// (~13 k clk) bound the kernels, not the tensor pipe (1.6 k clk per tile); 4 warpgroups instead of 2 were slower
+// (register pressure in the epilogue), so kNW = 2.
 #include <cmath>
 
 #include "attn_common.cuh"
@@ -40,7 +44,12 @@ struct BwdArgs {
     long long* dbg;      // optional [2 kernels][num CTAs][16] clock64 phase sums (tools/bwd_phase_timing.py)
 };
 
-constexpr int kBwdThreads = 320;
+#ifndef GTA_BWD_NW
+#define GTA_BWD_NW 2
+#endif
+constexpr int kNW = GTA_BWD_NW;                 // compute warpgroups per CTA (2 or 4); each owns kCW columns of every S / dP tile
+constexpr int kCW = 128 / kNW;
+constexpr int kBwdThreads = kNW * 128 + 64;
 constexpr uint32_t kBwdTmemS = 0, kBwdTmemDP = 128, kBwdTmemAcc0 = 256, kBwdTmemAcc1 = 384;
 
 template <int D>
@@ -49,9 +58,15 @@ struct BwdSmem {
     static constexpr uint32_t kFix0 = 0, kFix1 = kTile;          // the CTA's own two tiles (K',V' or Q',dO')
     static constexpr uint32_t kStg0 = 2 * kTile;                  // [2 stages] streamed tile 0 (Q' / K')
     static constexpr uint32_t kStg1 = 4 * kTile;                  // [2 stages] streamed tile 1 (dO' / V')
-    static constexpr uint32_t kLD = 6 * kTile;                    // float [2 warpgroups][2 buffers][lse*log2e 64 | delta 64]
-    static constexpr uint32_t kBars = kLD + 2 * 2 * 128 * 4;
-    enum : int { bFix = 0, bFull = 1, bEmpty = 3, bSFull = 5, bPReady = 6, bDone = 7, bCount = 8 };
+    // head dims <= 96: P / dS go through SHARED memory (two 32 KB K-major operand tiles, 128-byte swizzle) so that the
+    // S / dP accumulators are free the moment they are in registers and the next tile's S / dP MMAs overlap the SIMT
+    // phase; head dim 128 has no room for that and keeps P / dS in tensor memory (in place).
+    static constexpr bool kPS = D <= 96;
+    static constexpr uint32_t kP = 6 * kTile;                     // P  [2 blocks of 64][128 rows][128 B]
+    static constexpr uint32_t kDS = kP + (kPS ? 32768u : 0u);     // dS
+    static constexpr uint32_t kLD = kDS + (kPS ? 32768u : 0u);    // float [2 warpgroups][2 buffers][lse*log2e 64 | delta 64]
+    static constexpr uint32_t kBars = kLD + 2 * 2 * 128 * 4;      // kNW warpgroups x 2 buffers x 2 kCW floats = 512 floats
+    enum : int { bFix = 0, bFull = 1, bEmpty = 3, bSFull = 5, bPReady = 6, bDone = 7, bSFree = 8, bPdFree = 9, bCount = 10 };
     static constexpr uint32_t kTmemSlot = kBars + bCount * 8;
     static constexpr uint32_t kUsed = kTmemSlot + 16;
     static constexpr uint32_t kBytes = (kUsed + 1024 > 120u * 1024u) ? kUsed + 1024 : 120u * 1024u;
@@ -60,7 +75,7 @@ struct BwdSmem {
 __device__ __forceinline__ void bwd_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 // TMEM column of the packed bf16 A operand for K-step kk (16 rows of the streamed tile): the first compute warpgroup packs
 // columns 0..63 into 0..31, the second 64..127 into 64..95.
-__device__ __forceinline__ constexpr uint32_t pk_off(int kk) { return kk < 4 ? kk * 8u : 64u + (kk - 4) * 8u; }
+__device__ __forceinline__ constexpr uint32_t pk_off(int kk) { return (kk / (kCW / 16)) * kCW + (kk % (kCW / 16)) * 8u; }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -91,11 +106,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         mbar_init(&bars[L::bFix], 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&bars[L::bFull + s], 1); mbar_init(&bars[L::bEmpty + s], 1); }
         mbar_init(&bars[L::bSFull], 1);
-        mbar_init(&bars[L::bPReady], 256);
+        mbar_init(&bars[L::bPReady], kNW * 128);
         mbar_init(&bars[L::bDone], 1);
+        mbar_init(&bars[L::bSFree], kNW * 128);
+        mbar_init(&bars[L::bPdFree], 1);
         fence_mbar_init();
     }
-    if (warp == 8) {
+    if (warp == kNW * 4) {
         tmem_alloc(tmem_slot, kTmemCols);
         tmem_relinquish();
     }
@@ -104,8 +121,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
-    if (warp < 8) {
-        // =========================================================== two compute warpgroups: thread r <-> row r <-> TMEM
+    if (warp < kNW * 4) {
+        // =========================================================== kNW compute warpgroups: thread r <-> row r <-> TMEM
         // lane r in both; warpgroup w owns columns [64w, 64w+64) of every S / dP tile (no exchange is needed: lse and
         // delta are known), which halves the latency of the SIMT phase between the two MMA phases of a tile.
         const int wgc = warp >> 2;
@@ -118,22 +135,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         const float* del_bh = a.delta + bh * a.Tq;
         float my_lse2 = 0.f, my_del = 0.f;                   // dQ kernel: this row's statistics
         // dKV kernel: per-column statistics of this warpgroup's 64 query columns, [buffer][lse*log2e 64 | delta 64]
-        float* sLDw = sLD + wgc * 256;
+        float* sLDw = sLD + wgc * (4 * kCW);
         auto col_stat = [&](int i) {                         // thread r fetches one of the 128 values of query tile i
-            const int t = i * 128 + wgc * 64 + (r & 63);
-            if (t >= a.Tq) return 0.f;
-            return r < 64 ? lse_bh[t] * kLog2e : del_bh[t];
+            const int t = i * 128 + wgc * kCW + (r % kCW);
+            if (t >= a.Tq || r >= 2 * kCW) return 0.f;
+            return r < kCW ? lse_bh[t] * kLog2e : del_bh[t];
         };
         if (!kDKV) {
             const int t = tile * 128 + r;
             if (t < a.Tq) { my_lse2 = lse_bh[t] * kLog2e; my_del = del_bh[t]; }
         } else {
-            sLDw[r] = col_stat(0);
+            if (r < 2 * kCW) sLDw[r] = col_stat(0);
             bwd_bar_sync(1 + wgc);
         }
         // packed results go to the first 32 columns of the warpgroup's OWN 64-column range (columns 0..31 / 64..95):
         // never into columns the other warpgroup still has to read
-        const uint32_t pk_col = wgc * 64;
+        const uint32_t pk_col = wgc * kCW;
         const size_t cta = (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         long long* dbg = (a.dbg && threadIdx.x == 0) ? a.dbg + ((kDKV ? 0 : static_cast<size_t>(gridDim.x) * gridDim.y * gridDim.z) + cta) * 16 : nullptr;
         long long d_wait = 0, d_ld = 0, d_cmp = 0, d_st = 0;
@@ -158,7 +175,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                 }
                 if (a.dtc && a.hd.se3) {                     // ... and the raw se3 elements the trans_coeff term reads
                     const TIn* raw_ = kDKV
-                        ? (wgc == 0 ? reinterpret_cast<const TIn*>(a.v) + b * a.v_sb + h * a.v_sh + static_cast<int64_t>(tt_) * a.v_st
+                        ? (wgc < kNW / 2 ? reinterpret_cast<const TIn*>(a.v) + b * a.v_sb + h * a.v_sh + static_cast<int64_t>(tt_) * a.v_st
                                     : reinterpret_cast<const TIn*>(a.k) + b * a.k_sb + h * a.k_sh + static_cast<int64_t>(tt_) * a.k_st)
                         : reinterpret_cast<const TIn*>(a.q) + b * a.q_sb + h * a.q_sh + static_cast<int64_t>(tt_) * a.q_st;
                     for (int e = a.hd.triv; e < a.hd.triv + a.hd.se3; e += 128 / static_cast<int>(sizeof(TIn)))
@@ -170,23 +187,28 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
             mbar_wait(&bars[L::bSFull], i & 1);
             tc_fence_after();
             const long long d1 = dbg ? clock64() : 0;
-            const float* ld = sLDw + (i & 1) * 128;
-            const int ncol = (kDKV ? a.Tq : a.Tk) - i * 128 - wgc * 64;   // valid columns of this warpgroup's half
-            uint32_t sr[64], dr[64];
-            tmem_ld32(lane_base + kBwdTmemS + wgc * 64, sr);
-            tmem_ld32(lane_base + kBwdTmemS + wgc * 64 + 32, sr + 32);
-            tmem_ld32(lane_base + kBwdTmemDP + wgc * 64, dr);
-            tmem_ld32(lane_base + kBwdTmemDP + wgc * 64 + 32, dr + 32);
+            const float* ld = sLDw + (i & 1) * (2 * kCW);
+            const int ncol = (kDKV ? a.Tq : a.Tk) - i * 128 - wgc * kCW;   // valid columns of this warpgroup's half
+            uint32_t sr[kCW], dr[kCW];
+#pragma unroll
+            for (int q32 = 0; q32 < kCW / 32; ++q32) {
+                tmem_ld32(lane_base + kBwdTmemS + wgc * kCW + q32 * 32, sr + q32 * 32);
+                tmem_ld32(lane_base + kBwdTmemDP + wgc * kCW + q32 * 32, dr + q32 * 32);
+            }
             tmem_ld_wait();
+            if (L::kPS) {                                    // S / dP are in registers: the next tile's MMAs may overwrite them
+                tc_fence_before();
+                mbar_arrive(&bars[L::bSFree]);
+            }
             const long long d2 = dbg ? clock64() : 0;
             // dS = P * (dP - delta) * scale = P * (dP*scale - delta*scale): one FFMA + one FMUL per element
             const float my_dls = my_del * a.scale;
 #pragma unroll
-            for (int u4 = 0; u4 < 16; ++u4) {                // 4 columns per step (one 16-byte read of each statistic)
+            for (int u4 = 0; u4 < kCW / 4; ++u4) {           // 4 columns per step (one 16-byte read of each statistic)
                 float l2[4], dls[4];
                 if (kDKV) {
                     const float4 a4 = *reinterpret_cast<const float4*>(ld + 4 * u4);
-                    const float4 b4 = *reinterpret_cast<const float4*>(ld + 64 + 4 * u4);
+                    const float4 b4 = *reinterpret_cast<const float4*>(ld + kCW + 4 * u4);
                     l2[0] = a4.x; l2[1] = a4.y; l2[2] = a4.z; l2[3] = a4.w;
                     dls[0] = b4.x * a.scale; dls[1] = b4.y * a.scale; dls[2] = b4.z * a.scale; dls[3] = b4.w * a.scale;
                 } else {
@@ -204,9 +226,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                 sr[2 * u4] = pack_bf16x2(pv[0], pv[1]); sr[2 * u4 + 1] = pack_bf16x2(pv[2], pv[3]);
                 dr[2 * u4] = pack_bf16x2(dv[0], dv[1]); dr[2 * u4 + 1] = pack_bf16x2(dv[2], dv[3]);
             }
-            if (ncol < 64) {                                 // ragged last tile: zero the packed columns past the end
+            if (ncol < kCW) {                                // ragged last tile: zero the packed columns past the end
 #pragma unroll
-                for (int u = 0; u < 32; ++u) {
+                for (int u = 0; u < kCW / 2; ++u) {
                     if (2 * u + 1 >= ncol) {
                         const uint32_t keep = (2 * u < ncol) ? 0x0000FFFFu : 0u;
                         sr[u] &= keep; dr[u] &= keep;
@@ -214,14 +236,31 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                 }
             }
             const long long d3 = dbg ? clock64() : 0;
-            if (kDKV) tmem_st32(lane_base + kBwdTmemS + pk_col, sr);
-            tmem_st32(lane_base + (kDKV ? kBwdTmemDP : kBwdTmemS) + pk_col, dr);
-            tmem_st_wait();
-            tc_fence_before();
+            if (L::kPS) {
+                // the previous tile's dV/dK (dQ) MMAs must be done reading the shared P / dS tiles
+                if (i > 0) mbar_wait(&bars[L::bPdFree], (i - 1) & 1);
+#pragma unroll
+                for (int u = 0; u < kCW / 8; ++u) {          // chunks of 8 streamed rows (K elements)
+                    const uint32_t off = tile_sw128_offset(r, wgc * (kCW / 8) + u);
+                    if (kDKV) *reinterpret_cast<uint4*>(smem + L::kP + off) = make_uint4(sr[4 * u], sr[4 * u + 1], sr[4 * u + 2], sr[4 * u + 3]);
+                    *reinterpret_cast<uint4*>(smem + L::kDS + off) = make_uint4(dr[4 * u], dr[4 * u + 1], dr[4 * u + 2], dr[4 * u + 3]);
+                }
+                fence_proxy_async_smem();
+            } else {
+                if (kCW == 64) {
+                    if (kDKV) tmem_st32(lane_base + kBwdTmemS + pk_col, sr);
+                    tmem_st32(lane_base + (kDKV ? kBwdTmemDP : kBwdTmemS) + pk_col, dr);
+                } else {
+                    if (kDKV) tmem_st16(lane_base + kBwdTmemS + pk_col, sr);
+                    tmem_st16(lane_base + (kDKV ? kBwdTmemDP : kBwdTmemS) + pk_col, dr);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+            }
             mbar_arrive(&bars[L::bPReady]);
             if (dbg) { const long long d4 = clock64(); d_wait += d1 - d0; d_ld += d2 - d1; d_cmp += d3 - d2; d_st += d4 - d3; }
             if (kDKV && i + 1 < nstream) {
-                sLDw[((i + 1) & 1) * 128 + r] = nx_stat;
+                if (r < 2 * kCW) sLDw[((i + 1) & 1) * (2 * kCW) + r] = nx_stat;
                 bwd_bar_sync(1 + wgc);
             }
         }
@@ -243,9 +282,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         float dtc_part = 0.f;
         // dKV kernel: warpgroup 0 finishes dV' (accumulator 0), warpgroup 1 dK' (accumulator 1);
         // dQ kernel: the two warpgroups split the columns of dQ' (accumulator 0).
-        const int c_lo = kDKV ? 0 : wgc * (D / 16), c_hi = kDKV ? D / 8 : (wgc + 1) * (D / 16);
+        // dKV kernel: the first half of the warpgroups finishes dV' (accumulator 0), the second half dK' (accumulator 1),
+        // each warpgroup a contiguous share of the columns; dQ kernel: all warpgroups split the columns of dQ'.
+        constexpr int kShare = kDKV ? kNW / 2 : kNW;                 // warpgroups per accumulator
+        const int part = wgc % kShare;
+        const int c_lo = part * (D / 8) / kShare, c_hi = (part + 1) * (D / 8) / kShare;
         {
-            const int which = kDKV ? wgc : 0;
+            const int which = kDKV ? wgc / kShare : 0;
             const uint32_t acc = lane_base + (which == 0 ? kBwdTmemAcc0 : kBwdTmemAcc1);
             const bool rotate = kDKV ? (which == 1 || a.v_transform) : true;
             const TIn* raw = kDKV
@@ -312,10 +355,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
             }
             const long long t2_ = dbg ? clock64() : 0;
             // hand the staged rows to the cooperative store
-            if (kDKV) asm volatile("bar.sync %0, 128;" ::"r"(3 + wgc) : "memory");
-            else asm volatile("bar.sync 3, 256;" ::: "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(3 + which), "r"(kShare * 128) : "memory");
             constexpr int kPieces = D * static_cast<int>(sizeof(TOut)) / 16;      // 16-byte pieces per row
-            const int nthr = kDKV ? 128 : 256, tid = kDKV ? r : static_cast<int>(threadIdx.x);
+            const int nthr = kShare * 128, tid = part * 128 + r;
             const int nrows = min(128, T - tile * 128);
             TOut* gbase = reinterpret_cast<TOut*>(kDKV ? (which == 0 ? a.dv : a.dk) : a.dq);
             for (int idx = tid; idx < nrows * kPieces; idx += nthr) {
@@ -335,21 +377,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
             dbg[0] = d_end - d_start; dbg[1] = d_wait; dbg[2] = d_ld; dbg[3] = d_cmp; dbg[4] = d_st;
             dbg[5] = d_end - d_loop_end; dbg[6] = nstream; dbg[7] = d_done - d_loop_end;
         }
-    } else if (warp == 8) {
+    } else if (warp == kNW * 4) {
         // =========================================================== UMMA issuer
         constexpr uint32_t idesc_ss = make_idesc_bf16(128, 128, 0, 0);
         constexpr uint32_t idesc_ts = make_idesc_bf16(128, D, 0, 1);
         const uint32_t f0 = smem_u32(smem + L::kFix0), f1 = smem_u32(smem + L::kFix1);
         mbar_wait(&bars[L::bFix], 0);
-#pragma unroll 1
-        for (int i = 0; i < nstream; ++i) {
+        const uint32_t p_sm = smem_u32(smem + L::kP), ds_sm = smem_u32(smem + L::kDS);
+        // S / dP of streamed tile i:  dKV: S^T = K' Q'^T, dP^T = V' dO'^T;  dQ: S = Q' K'^T, dP = dO' V'^T  (A = fixed, B = streamed)
+        auto issue_sdp = [&](int i) {
             const int s = i & 1;
             const uint32_t g0 = smem_u32(smem + L::kStg0 + s * L::kTile), g1 = smem_u32(smem + L::kStg1 + s * L::kTile);
             mbar_wait(&bars[L::bFull + s], (i >> 1) & 1);
             tc_fence_after();
             if (elect_one()) {
-                // dKV: S^T = K' Q'^T, dP^T = V' dO'^T   (A = fixed tile, B = streamed tile)
-                // dQ : S   = Q' K'^T, dP   = dO' V'^T   (A = fixed tile, B = streamed tile)
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk)
                     umma_ss(tmem_base + kBwdTmemS, desc_kmajor_sw64(f0, kk), desc_kmajor_sw64(g0, kk), idesc_ss, kk > 0);
@@ -359,28 +400,46 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                 umma_commit(&bars[L::bSFull]);
             }
             __syncwarp();
+        };
+        if (L::kPS) issue_sdp(0);
+#pragma unroll 1
+        for (int i = 0; i < nstream; ++i) {
+            const int s = i & 1;
+            const uint32_t g0 = smem_u32(smem + L::kStg0 + s * L::kTile), g1 = smem_u32(smem + L::kStg1 + s * L::kTile);
+            if (L::kPS) {
+                if (i + 1 < nstream) {                       // next tile's S / dP as soon as this tile's are in registers
+                    mbar_wait(&bars[L::bSFree], i & 1);
+                    issue_sdp(i + 1);
+                }
+            } else {
+                issue_sdp(i);
+            }
             mbar_wait(&bars[L::bPReady], i & 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t accf = (i > 0) ? 1u : 0u;
                 if (kDKV) {
-                    // dV' += P^T dO'   (A = P^T in TMEM, B = dO'_i read MN-major);  dK' += dS^T Q'
+                    // dV' += P^T dO'   (A = P^T, B = dO'_i read MN-major);  dK' += dS^T Q'
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + pk_off(kk), desc_mnmajor_sw64(g1, kk), idesc_ts,
-                                (kk > 0) ? 1u : accf);
+                    for (int kk = 0; kk < 8; ++kk) {
+                        if (L::kPS) umma_ss(tmem_base + kBwdTmemAcc0, desc_p_sw128(p_sm, kk), desc_mnmajor_sw64(g1, kk), idesc_ts, (kk > 0) ? 1u : accf);
+                        else umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + pk_off(kk), desc_mnmajor_sw64(g1, kk), idesc_ts, (kk > 0) ? 1u : accf);
+                    }
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        umma_ts(tmem_base + kBwdTmemAcc1, tmem_base + kBwdTmemDP + pk_off(kk), desc_mnmajor_sw64(g0, kk), idesc_ts,
-                                (kk > 0) ? 1u : accf);
+                    for (int kk = 0; kk < 8; ++kk) {
+                        if (L::kPS) umma_ss(tmem_base + kBwdTmemAcc1, desc_p_sw128(ds_sm, kk), desc_mnmajor_sw64(g0, kk), idesc_ts, (kk > 0) ? 1u : accf);
+                        else umma_ts(tmem_base + kBwdTmemAcc1, tmem_base + kBwdTmemDP + pk_off(kk), desc_mnmajor_sw64(g0, kk), idesc_ts, (kk > 0) ? 1u : accf);
+                    }
                 } else {
-                    // dQ' += dS K'     (A = dS in TMEM, B = K'_j read MN-major)
+                    // dQ' += dS K'     (A = dS, B = K'_j read MN-major)
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + pk_off(kk), desc_mnmajor_sw64(g0, kk), idesc_ts,
-                                (kk > 0) ? 1u : accf);
+                    for (int kk = 0; kk < 8; ++kk) {
+                        if (L::kPS) umma_ss(tmem_base + kBwdTmemAcc0, desc_p_sw128(ds_sm, kk), desc_mnmajor_sw64(g0, kk), idesc_ts, (kk > 0) ? 1u : accf);
+                        else umma_ts(tmem_base + kBwdTmemAcc0, tmem_base + kBwdTmemS + pk_off(kk), desc_mnmajor_sw64(g0, kk), idesc_ts, (kk > 0) ? 1u : accf);
+                    }
                 }
                 umma_commit(&bars[L::bEmpty + s]);
+                if (L::kPS) umma_commit(&bars[L::bPdFree]);
                 if (i == nstream - 1) umma_commit(&bars[L::bDone]);
             }
             __syncwarp();
@@ -406,7 +465,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kNW * 4) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
