@@ -38,6 +38,13 @@ class PackedReps:
     n_q_views: int = 1
     n_k_views: int = 1
 
+    _TABLES = ("se3_q", "se3_k", "so3_q", "so3_k", "so2_q", "so2_k", "se3_qi", "t2_q", "t2_k")
+
+    def batch_slice(self, lo: int, hi: int) -> "PackedReps":
+        """The tables of batch elements [lo, hi) (views: every table has the batch as its leading dim)."""
+        kw = {n: (None if getattr(self, n) is None else getattr(self, n)[lo:hi]) for n in self._TABLES}
+        return PackedReps(n_q_views=self.n_q_views, n_k_views=self.n_k_views, **kw)
+
     def c_struct(self) -> GtaReps:
         return GtaReps(*[_ptr(getattr(self, n)) for n in ("se3_q", "se3_k", "so3_q", "so3_k", "so2_q", "so2_k",
                                                            "se3_qi", "t2_q", "t2_k")])
@@ -124,16 +131,20 @@ def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: P
                       trans_coeff: Optional[torch.Tensor] = None, scale: Optional[float] = None,
                       v_transform: bool = True, out_dtype: Optional[torch.dtype] = None,
                       return_lse: bool = False, flags: int = 0, debug_clocks: Optional[torch.Tensor] = None,
-                      euclid: bool = False):
+                      euclid: bool = False, out: Optional[torch.Tensor] = None):
     """q [B,H,Tq,D], k,v [B,H,Tk,D] (strided views allowed) -> out [B,H,Tq,D] as a permuted view of a
-    contiguous [B,Tq,H,D] buffer (so the reference's 'b h n d -> b n (h d)' is free)."""
+    contiguous [B,Tq,H,D] buffer (so the reference's 'b h n d -> b n (h d)' is free).  `out`: optional preallocated
+    contiguous [B,Tq,H,D] destination."""
     B, H, Tq, D = q.shape
     dev = q.device
     if scale is None:
         scale = D ** -0.5
     if trans_coeff is not None:
         trans_coeff = trans_coeff.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
-    out = torch.empty(B, Tq, H, D, device=dev, dtype=out_dtype or q.dtype)
+    if out is None:
+        out = torch.empty(B, Tq, H, D, device=dev, dtype=out_dtype or q.dtype)
+    else:
+        assert out.shape == (B, Tq, H, D) and out.is_contiguous() and out.device == dev, "out must be contiguous [B,Tq,H,D]"
     lse = torch.empty(B, H, Tq, device=dev, dtype=torch.float32) if return_lse else None
     p = _params(q, k, v, out, reps, f_dims, trans_coeff, scale, v_transform, flags, lse, euclid)
     nbytes = lib().gta_attn_fwd_workspace_bytes_p(p)

@@ -500,3 +500,24 @@ def test_backward_abi_direct_and_linearity():
         assert a.shape == q.shape
         assert (2 * a.float() - b.float()).abs().max() <= 2e-2 * b.float().abs().max()
     assert abs(2 * float(g1[3]) - float(g2[3])) <= 2e-2 * abs(float(g2[3])) + 1e-4
+
+
+def test_host_pipeline_matches_device_call():
+    """gta_b200.host.HostStagedAttention (pinned host buffers, batch chunks over three streams) is bit-identical to the
+    device-resident call on the same inputs, for self- and cross-attention."""
+    from gta_b200.host import HostStagedAttention
+    for cross in (False, True):
+        cfg = GtaConfig(**MSN_SO3, n_q_views=3 if cross else 2, n_k_views=2)
+        B, tq, tk = 6, (40 if cross else 64), 64
+        inp = make_inputs(cfg, B, tq, tk, cross=cross, seed=51, dtype=torch.bfloat16)
+        base = lambda t: t if t._base is None else base(t._base)
+        bufs = ({"q": base(inp["q"]).pin_memory(), "kv": base(inp["k"]).pin_memory()} if cross
+                else {"qkv": base(inp["q"]).pin_memory()})
+        small = {n: inp[n].contiguous().pin_memory() for n in (("extr_k", "coord_k", "extr_q", "coord_q") if cross
+                                                                  else ("extr_k", "coord_k"))}
+        out_host = torch.empty(B, cfg.n_q_views * tq, cfg.heads, cfg.head_dim, dtype=torch.bfloat16).pin_memory()
+        pipe = HostStagedAttention(cfg, bufs, small, out_host, torch.device("cuda", 0), chunks=4)
+        pipe.run()
+        torch.cuda.synchronize()
+        ref = _run(cfg, inp)                                  # [B,H,Tq,D]
+        assert np.array_equal(out_host.permute(0, 2, 1, 3).float().numpy(), ref)
