@@ -443,7 +443,9 @@ def _grad_oracle(cfg, inp, tc, dout):
     (CLEVR, 3, 2, 171, 300, True, 1, torch.bfloat16, 0.5, True),        # D = 64, views straddle tiles, Tq = 513
     (CLEVR, 2, 2, 150, 150, False, 1, torch.bfloat16, 0.5, False),      # v_transform = False
     (MSN_SO3, 3, 2, 40, 64, True, 1, torch.float32, 0.3, True),         # fp32 I/O (bf16 tensor-core math in the backward)
-], ids=["cfg1b", "msn_cross", "msn_enc", "clevr_dec", "clevr_novt", "msn_cross_f32"])
+    (CLEVR, 3, 2, 853, 300, True, 1, torch.bfloat16, 0.01, True),       # CLEVR decoder shape (Tq = 2559, ragged everywhere)
+    (MSN_SO3, 5, 5, 512, 256, True, 1, torch.bfloat16, 0.01, True),     # MSN decoder shape (Tq = 2560, Tk = 1280)
+], ids=["cfg1b", "msn_cross", "msn_enc", "clevr_dec", "clevr_novt", "msn_cross_f32", "clevr_dec_full", "msn_dec_full"])
 def test_fused_backward_matches_autograd_oracle(case):
     """dq, dk, dv and d(trans_coeff) of the fused backward, through the public drop-in under autograd, against fp64
     autograd of the oracle on the same (rounded) inputs.  bf16 tensor-core math: errors relative to the gradient scale."""
