@@ -134,18 +134,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         const float* lse_bh = a.lse + bh * a.Tq;
         const float* del_bh = a.delta + bh * a.Tq;
         float my_lse2 = 0.f, my_del = 0.f;                   // dQ kernel: this row's statistics
-        // dKV kernel: per-column statistics of this warpgroup's 64 query columns, [buffer][lse*log2e 64 | delta 64]
+        // dKV kernel: per-column statistics of this warpgroup's kCW query columns, [buffer][lse*log2e | delta*scale]
         float* sLDw = sLD + wgc * (4 * kCW);
-        auto col_stat = [&](int i) {                         // thread r fetches one of the 128 values of query tile i
+        // thread r fetches one of the 2*kCW values of query tile i.  The RAW value is returned and scaled only when it
+        // is stored (col_scale): an arithmetic use right after the load would stall the in-order issue for a full
+        // global-memory latency at the top of every tile (measured: 1.5 k clk per tile).
+        auto col_stat = [&](int i) {
             const int t = i * 128 + wgc * kCW + (r % kCW);
             if (t >= a.Tq || r >= 2 * kCW) return 0.f;
-            return r < kCW ? lse_bh[t] * kLog2e : del_bh[t];
+            return r < kCW ? lse_bh[t] : del_bh[t];
         };
+        const float col_scale = r < kCW ? kLog2e : a.scale;  // lse in log2 units; delta pre-scaled: dS = P * (dP*scale - delta*scale)
         if (!kDKV) {
             const int t = tile * 128 + r;
             if (t < a.Tq) { my_lse2 = lse_bh[t] * kLog2e; my_del = del_bh[t]; }
         } else {
-            if (r < 2 * kCW) sLDw[r] = col_stat(0);
+            if (r < 2 * kCW) sLDw[r] = col_stat(0) * col_scale;
             bwd_bar_sync(1 + wgc);
         }
         // packed results go to the first 32 columns of the warpgroup's OWN 64-column range (columns 0..31 / 64..95):
@@ -153,14 +157,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
         const uint32_t pk_col = wgc * kCW;
         const size_t cta = (static_cast<size_t>(blockIdx.z) * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         long long* dbg = (a.dbg && threadIdx.x == 0) ? a.dbg + ((kDKV ? 0 : static_cast<size_t>(gridDim.x) * gridDim.y * gridDim.z) + cta) * 16 : nullptr;
-        long long d_wait = 0, d_ld = 0, d_cmp = 0, d_st = 0;
+        long long d_wait = 0, d_ld = 0, d_cmp = 0, d_st = 0, d_tail = 0;
         const long long d_start = dbg ? clock64() : 0;
 #pragma unroll 1
         for (int i = 0; i < nstream; ++i) {
             float nx_stat = 0.f;
             if (kDKV && i + 1 < nstream) nx_stat = col_stat(i + 1);   // in flight during this tile
             if (i == nstream - 1) {
-                // pull this row's epilogue operands (view matrices, SO(2) table) into L1 while the last tile is computed
+                // pull this row's epilogue operands (view matrices, raw se3 elements) into L1 while the last tile is computed
+                // (not the per-row SO(2) tables: 3 lines per row x 256 rows would evict everything else from the ~30 KB of L1)
                 const int T_ = kDKV ? a.Tk : a.Tq;
                 const int tt_ = min(tile * 128 + r, T_ - 1);
                 const size_t view_ = static_cast<size_t>(b) * (kDKV ? a.Nk : a.Nq) + tt_ / (kDKV ? a.tpvk : a.tpvq);
@@ -168,10 +173,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                 if (a.hd.so3) {
                     prefetch_l1((kDKV ? a.so3_k : a.so3_q) + view_ * 34);
                     prefetch_l1((kDKV ? a.so3_k : a.so3_q) + view_ * 34 + 32);
-                }
-                if (a.hd.so2) {
-                    const float* so2_ = (kDKV ? a.so2_k : a.so2_q) + (static_cast<size_t>(b) * T_ + tt_) * a.C * 2;
-                    for (int off = 0; off < a.C * 2; off += 32) prefetch_l1(so2_ + off);
                 }
                 if (a.dtc && a.hd.se3) {                     // ... and the raw se3 elements the trans_coeff term reads
                     const TIn* raw_ = kDKV
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                     const float4 a4 = *reinterpret_cast<const float4*>(ld + 4 * u4);
                     const float4 b4 = *reinterpret_cast<const float4*>(ld + kCW + 4 * u4);
                     l2[0] = a4.x; l2[1] = a4.y; l2[2] = a4.z; l2[3] = a4.w;
-                    dls[0] = b4.x * a.scale; dls[1] = b4.y * a.scale; dls[2] = b4.z * a.scale; dls[3] = b4.w * a.scale;
+                    dls[0] = b4.x; dls[1] = b4.y; dls[2] = b4.z; dls[3] = b4.w;
                 } else {
 #pragma unroll
                     for (int w = 0; w < 4; ++w) { l2[w] = my_lse2; dls[w] = my_dls; }
@@ -259,10 +260,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
             }
             mbar_arrive(&bars[L::bPReady]);
             if (dbg) { const long long d4 = clock64(); d_wait += d1 - d0; d_ld += d2 - d1; d_cmp += d3 - d2; d_st += d4 - d3; }
+            const long long d5 = dbg ? clock64() : 0;
             if (kDKV && i + 1 < nstream) {
-                if (r < 2 * kCW) sLDw[((i + 1) & 1) * (2 * kCW) + r] = nx_stat;
+                asm volatile("" : "+f"(nx_stat));            // first use of the loaded value HERE (keeps ptxas from scaling it early)
+                if (r < 2 * kCW) sLDw[((i + 1) & 1) * (2 * kCW) + r] = nx_stat * col_scale;
                 bwd_bar_sync(1 + wgc);
             }
+            if (dbg) d_tail += clock64() - d5;
         }
 
         // ---- epilogue: accumulators -> registers (8 columns at a time) -> transposed / inverse rep -> global
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
                 TOut* grow = gbase + ((static_cast<int64_t>(b) * T + tile * 128 + row) * a.H + h) * D;
                 *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(grow) + pc * 16) = val;
             }
-            if (dbg) { dbg[8] = e_wait; dbg[9] = e_cmp; dbg[10] = clock64() - t2_; dbg[11] = t2_ - d_done; }
+            if (dbg) { dbg[8] = e_wait; dbg[9] = e_cmp; dbg[10] = clock64() - t2_; dbg[11] = t2_ - d_done; dbg[12] = d_tail; dbg[13] = d_loop_end - d_start; }
         }
         if (a.dtc) {
             dtc_part = warp_sum(dtc_part);

@@ -43,6 +43,7 @@ def main():
               f" (tensor work per tile {(12 * 64 + (16 if 'dKV' in nme else 8) * 51)} clk)")
         for i, lab in ((1, "wait for S/dP (MMA + wake-up)"), (2, "tcgen05.ld 4 x 32 columns"), (3, "P / dS computation"), (4, "tcgen05.st + fence + arrive")):
             print(f"    {lab:32s} {(part[:, i] / n).mean():7.0f} clk per tile")
+        print(f"    {'next-tile statistics + barrier':32s} {(part[:, 12] / n).mean():7.0f} clk per tile;  whole loop {(part[:, 13] / n).mean():.0f} clk per tile")
         print(f"    epilogue parts: setup+chunk loop {part[:, 11].mean():.0f} (tcgen05.wait::ld {part[:, 8].mean():.0f}, rotate+stage {part[:, 9].mean():.0f}), barrier + coalesced store {part[:, 10].mean():.0f}")
         print(f"    {'epilogue (after the last tile)':32s} {part[:, 5].mean():7.0f} clk per CTA, of which {part[:, 7].mean():.0f} waiting for the last MMAs")
 
