@@ -34,6 +34,7 @@ int launch_rotate_debug_generic(const GtaAttnParams& p, float* qt, float* kt, fl
 
 int validate_attn_params(const GtaAttnParams* p);
 int launch_rotate_kv(const GtaAttnParams& p, cudaStream_t st);
+int launch_rotate_q_do(const GtaAttnParams& p, const void* dout, uint8_t* q_img, uint8_t* do_img, cudaStream_t st);
 int launch_rotate_debug(const GtaAttnParams& p, float* qt, float* kt, float* vt, cudaStream_t st);
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);

@@ -476,78 +476,54 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(const BwdArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------- staging
-struct BwdStageArgs {
-    const void* x; int64_t sb, sh, st;     // rows [B,H,T,D] (strided)
-    uint8_t* img;                          // [B*H*ntiles] tile images
-    int B, H, T, D, N, tpv, ntiles, C;
-    HeadDims hd;
-    const float* se3; const float* so3; const float* so2; const float* tc_ptr;
-    int rotate;
-};
-
-// One thread per (row, 8-element chunk): raw row -> rho_q^{-T} -> bf16 operand tile image (zero rows past T).
-template <typename T>
-__global__ void bwd_stage_rows_kernel(const BwdStageArgs a) {
-    const int nch = a.D >> 3;
-    const int64_t total = static_cast<int64_t>(a.B) * a.H * a.ntiles * 128 * nch;
-    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int c = static_cast<int>(i % nch);
-    int64_t rr = i / nch;
-    const int row = static_cast<int>(rr % 128); rr /= 128;
-    const int tile = static_cast<int>(rr % a.ntiles); rr /= a.ntiles;
-    const int h = static_cast<int>(rr % a.H);
-    const int b = static_cast<int>(rr / a.H);
-    const int t = tile * 128 + row;
-    float x[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) x[u] = 0.f;
-    if (t < a.T) {
-        load_chunk<T>(reinterpret_cast<const T*>(a.x) + b * a.sb + h * a.sh + static_cast<int64_t>(t) * a.st + c * 8, x);
-        if (a.rotate) {
-            const size_t view = static_cast<size_t>(b) * a.N + t / a.tpv;
-            apply_rep_chunk<kModeQ>(x, c, a.hd, a.se3 + view * 16, a.so3 + view * 34,
-                                    a.so2 + (static_cast<size_t>(b) * a.T + t) * a.C * 2, a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f);
-        }
-    }
-    uint8_t* dst = a.img + ((static_cast<size_t>(b) * a.H + h) * a.ntiles + tile) * (static_cast<size_t>(128) * a.D * 2);
-    *reinterpret_cast<uint4*>(dst + tile_sw64_offset(row, c)) = pack_chunk_bf16(x);
-}
-
 // delta[b,h,t] = sum_d dO * O, and the output-side trans_coeff term: O_i = sum_j M_ij O'_j + tc * M_i3 * O'_3 (i < 3),
-// O_3 = M_33 O'_3 with M = E_q  =>  d/dtc = sum_{i<3} dO_i M_i3 O_3 / M_33 per SE(3) 4-vector.  One thread per row.
+// O_3 = M_33 O'_3 with M = E_q  =>  d/dtc = sum_{i<3} dO_i M_i3 O_3 / M_33 per SE(3) 4-vector.
+// 16 lanes per row (one 16-byte chunk each, D <= 128), two rows per warp: coalesced reads, shuffle reduction.
 template <typename T>
 __global__ void bwd_delta_kernel(const T* __restrict__ out, const T* __restrict__ dout, float* __restrict__ delta,
                                  float* dtc, const float* __restrict__ se3_q, int B, int Tq, int H, int D, int Nq, int tpvq,
                                  int triv, int se3, int v_transform) {
-    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int64_t total = static_cast<int64_t>(B) * Tq * H;
+    const int c = threadIdx.x & 15;
     float part = 0.f;
-    if (i < total) {
-        const int h = static_cast<int>(i % H);
-        const int64_t bt = i / H;
+    // grid-stride over groups of 16 rows per block: the trans_coeff partial sums stay in registers and cost ONE atomic per
+    // block at the end (one atomic per warp on a single address serialised in L2: +0.25 ms at the MSN shape)
+    for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; row < ((total + 15) & ~15LL);
+         row += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 4) {
+    float acc = 0.f;
+    if (row < total && c * 8 < D) {
+        const int64_t bt = row / H;
         const int t = static_cast<int>(bt % Tq), b = static_cast<int>(bt / Tq);
-        const T* o = out + i * D;
-        const T* g = dout + i * D;
-        const float* M = se3_q + (static_cast<size_t>(b) * Nq + t / tpvq) * 16;
-        float acc = 0.f;
-        for (int c = 0; c < D / 8; ++c) {
-            float xo[8], xg[8];
-            load_chunk<T>(o + c * 8, xo);
-            load_chunk<T>(g + c * 8, xg);
+        float xo[8], xg[8];
+        load_chunk<T>(out + row * D + c * 8, xo);
+        load_chunk<T>(dout + row * D + c * 8, xg);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc = fmaf(xo[u], xg[u], acc);
-            if (dtc && v_transform && se3 && c * 8 >= triv && c * 8 < triv + se3) {
+        for (int u = 0; u < 8; ++u) acc = fmaf(xo[u], xg[u], acc);
+        if (dtc && v_transform && se3 && c * 8 >= triv && c * 8 < triv + se3) {
+            const float* M = se3_q + (static_cast<size_t>(b) * Nq + t / tpvq) * 16;
 #pragma unroll
-                for (int v4 = 0; v4 < 2; ++v4)
-                    part += (xg[4 * v4] * M[3] + xg[4 * v4 + 1] * M[7] + xg[4 * v4 + 2] * M[11]) * xo[4 * v4 + 3] / M[15];
-            }
+            for (int v4 = 0; v4 < 2; ++v4)
+                part += (xg[4 * v4] * M[3] + xg[4 * v4 + 1] * M[7] + xg[4 * v4 + 2] * M[11]) * xo[4 * v4 + 3] / M[15];
         }
-        delta[(static_cast<int64_t>(b) * H + h) * Tq + t] = acc;
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (row < total && c == 0) {
+        const int h = static_cast<int>(row % H);
+        const int64_t bt = row / H;
+        delta[(static_cast<int64_t>(bt / Tq) * H + h) * Tq + bt % Tq] = acc;
+    }
     }
     if (dtc) {
+        __shared__ float red[8];
         part = warp_sum(part);
-        if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(dtc, part);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            if (s != 0.f) atomicAdd(dtc, s);
+        }
     }
 }
 
@@ -613,25 +589,16 @@ int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st) {
     if (rc) return rc;
 
     const bool bf = p.in_dtype == GTA_DTYPE_BF16;
-    BwdStageArgs sa;
-    sa.B = p.B; sa.H = p.H; sa.T = p.Tq; sa.D = p.D; sa.N = p.Nq; sa.tpv = p.Tq / p.Nq; sa.ntiles = ntq; sa.C = p.so2 >> 1;
-    sa.hd = HeadDims{p.triv, p.se3, p.so3, p.so2};
-    sa.se3 = p.reps.se3_q; sa.so3 = p.reps.so3_q; sa.so2 = p.reps.so2_q; sa.tc_ptr = p.trans_coeff;
-    const int64_t total = static_cast<int64_t>(p.B) * p.H * ntq * 128 * (p.D >> 3);
-    const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-    sa.x = p.q; sa.sb = p.q_stride_b; sa.sh = p.q_stride_h; sa.st = p.q_stride_t; sa.img = q_img; sa.rotate = 1;
-    if (bf) bwd_stage_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(sa); else bwd_stage_rows_kernel<float><<<blocks, 256, 0, st>>>(sa);
-    // dO' = rho_q^{-T} dO: dout is [B,Tq,H,D] contiguous
-    sa.x = bp.dout; sa.sb = static_cast<int64_t>(p.Tq) * p.H * p.D; sa.sh = p.D; sa.st = static_cast<int64_t>(p.H) * p.D;
-    sa.img = do_img; sa.rotate = p.v_transform;
-    if (bf) bwd_stage_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(sa); else bwd_stage_rows_kernel<float><<<blocks, 256, 0, st>>>(sa);
+    rc = launch_rotate_q_do(p, bp.dout, q_img, do_img, st);      // Q' and dO' = rho_q^{-T} (q, dout): one launch, shared rep data
+    if (rc) return rc;
     {
         const int64_t rows = static_cast<int64_t>(p.B) * p.Tq * p.H;
-        const unsigned nb = static_cast<unsigned>((rows + 127) / 128);
+        const int64_t want = (rows * 16 + 255) / 256;
+        const unsigned nb = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
         float* dtc = p.se3 ? bp.dtrans_coeff : nullptr;
-        if (bf) bwd_delta_kernel<__nv_bfloat16><<<nb, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(p.out), static_cast<const __nv_bfloat16*>(bp.dout),
+        if (bf) bwd_delta_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p.out), static_cast<const __nv_bfloat16*>(bp.dout),
                                                                     delta, dtc, p.reps.se3_q, p.B, p.Tq, p.H, p.D, p.Nq, p.Tq / p.Nq, p.triv, p.se3, p.v_transform);
-        else bwd_delta_kernel<float><<<nb, 128, 0, st>>>(static_cast<const float*>(p.out), static_cast<const float*>(bp.dout), delta, dtc,
+        else bwd_delta_kernel<float><<<nb, 256, 0, st>>>(static_cast<const float*>(p.out), static_cast<const float*>(bp.dout), delta, dtc,
                                                          p.reps.se3_q, p.B, p.Tq, p.H, p.D, p.Nq, p.Tq / p.Nq, p.triv, p.se3, p.v_transform);
     }
     rc = check_launch("gta_attn_bwd (staging)");

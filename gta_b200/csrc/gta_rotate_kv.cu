@@ -37,7 +37,11 @@ __device__ __forceinline__ void split_chunk_bf16(const float* x, uint4& hi, uint
 // one is consumed: ~2*kUnroll 16-byte loads in flight per thread keep HBM busy at low occupancy cost.
 constexpr int kRotUnroll = 3;
 
-template <typename T>
+// kQSide = false: K' = rho_k K, V' = rho_k V (forward and backward staging).
+// kQSide = true : the same walk applied to the QUERY side of the backward: Q' = rho_q^{-T} Q and dO' = rho_q^{-T} dO share
+// their rep data exactly as K and V do (the "k" slot carries q, the "v" slot dout, v_transform gates the dO' rotation);
+// only the SE(3) block differs (transposed matrix).
+template <typename T, bool kQSide>
 __global__ void __launch_bounds__(128) rotate_kv_kernel(const RotArgs a) {
     const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -92,8 +96,13 @@ __global__ void __launch_bounds__(128) rotate_kv_kernel(const RotArgs a) {
                             float4 q4 = __ldg(reinterpret_cast<const float4*>(se3) + i);
                             M[4 * i] = q4.x; M[4 * i + 1] = q4.y; M[4 * i + 2] = q4.z; M[4 * i + 3] = q4.w;
                         }
-                        se3_apply(xk, M, tc);
-                        if (a.v_transform) se3_apply(xv, M, tc);
+                        if (kQSide) {
+                            se3_apply_T(xk, M, tc);
+                            if (a.v_transform) se3_apply_T(xv, M, tc);
+                        } else {
+                            se3_apply(xk, M, tc);
+                            if (a.v_transform) se3_apply(xv, M, tc);
+                        }
                     } else if (seg == 2) {
                         float W[34];
 #pragma unroll
@@ -183,9 +192,27 @@ int launch_rotate_kv(const GtaAttnParams& p, cudaStream_t st) {
     a.se3_k = p.reps.se3_k; a.so3_k = p.reps.so3_k; a.so2_k = p.reps.so2_k;
     a.tc_ptr = p.trans_coeff; a.C = p.so2 >> 1; a.v_transform = p.v_transform;
     dim3 grid(a.ntiles, p.H, p.B);
-    if (p.in_dtype == GTA_DTYPE_BF16) rotate_kv_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(a);
-    else rotate_kv_kernel<float><<<grid, 128, 0, st>>>(a);
+    if (p.in_dtype == GTA_DTYPE_BF16) rotate_kv_kernel<__nv_bfloat16, false><<<grid, 128, 0, st>>>(a);
+    else rotate_kv_kernel<float, false><<<grid, 128, 0, st>>>(a);
     return check_launch("gta_rotate_kv");
+}
+
+// Backward staging of the query side: Q' and dO' tile images (bf16) from q (strided) and dout [B,Tq,H,D].
+int launch_rotate_q_do(const GtaAttnParams& p, const void* dout, uint8_t* q_img, uint8_t* do_img, cudaStream_t st) {
+    RotArgs a;
+    a.k = p.q; a.v = dout;
+    a.k_sb = p.q_stride_b; a.k_sh = p.q_stride_h; a.k_st = p.q_stride_t;
+    a.v_sb = static_cast<int64_t>(p.Tq) * p.H * p.D; a.v_sh = p.D; a.v_st = static_cast<int64_t>(p.H) * p.D;
+    a.ntiles = num_kv_tiles(p.Tq);
+    a.ws_k = q_img; a.ws_v = do_img; a.lo_offset = 0;
+    a.H = p.H; a.Tk = p.Tq; a.D = p.D; a.Nk = p.Nq; a.tpv = p.Tq / p.Nq;
+    a.hd = HeadDims{p.triv, p.se3, p.so3, p.so2};
+    a.se3_k = p.reps.se3_q; a.so3_k = p.reps.so3_q; a.so2_k = p.reps.so2_q;
+    a.tc_ptr = p.trans_coeff; a.C = p.so2 >> 1; a.v_transform = p.v_transform;
+    dim3 grid(a.ntiles, p.H, p.B);
+    if (p.in_dtype == GTA_DTYPE_BF16) rotate_kv_kernel<__nv_bfloat16, true><<<grid, 128, 0, st>>>(a);
+    else rotate_kv_kernel<float, true><<<grid, 128, 0, st>>>(a);
+    return check_launch("gta_attn_bwd (Q'/dO' staging)");
 }
 
 int launch_rotate_debug(const GtaAttnParams& p, float* qt, float* kt, float* vt, cudaStream_t st) {
