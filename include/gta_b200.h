@@ -28,7 +28,7 @@ extern "C" {
 #define GTA_OK 0
 #define GTA_ERR_INVALID (-1)      /* bad argument / unsupported shape */
 #define GTA_ERR_CUDA (-2)         /* CUDA runtime error (message has the cudaError string) */
-#define GTA_ERR_UNSUPPORTED (-3)  /* valid in the reference but not implemented here (t2, euclid, ...) */
+#define GTA_ERR_UNSUPPORTED (-3)  /* valid in the reference but not implemented here (head dim, fp16, backward of the generic path, ...) */
 
 #define GTA_DTYPE_BF16 0
 #define GTA_DTYPE_F32 1

@@ -45,9 +45,9 @@ def gta_attention(cfg, q, k, v, extr_q, extr_k, coord_q, coord_k, trans_coeff=0.
     out = np.empty_like(q)
     rot = [np.empty_like(q), np.empty_like(k), np.empty_like(v)] if return_rotated else [None] * 3
     pf = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if a is not None else None
-    rc = lib().oracle_gta_attention(
+    rc = lib().oracle_gta_attention_ex(
         pq, pk, pv, peq, pek, pcq, pck,
-        B, H, Tq, Tk, D, eq.shape[1], ek.shape[1], triv, se3, so3, so2,
+        B, H, Tq, Tk, D, eq.shape[1], ek.shape[1], triv, se3, so3, so2, int(cfg.t2_dim()), int(bool(cfg.euclid)),
         int(cfg.so2), ctypes.c_float(cfg.max_freq_h), ctypes.c_float(cfg.max_freq_w),
         int(cfg.shared_freqs), ctypes.c_float(trans_coeff), ctypes.c_float(cfg.head_dim ** -0.5 / tau),
         int(cfg.v_transform), pf(out), pf(rot[0]), pf(rot[1]), pf(rot[2]))

@@ -46,11 +46,6 @@ def _run(cfg, inp, tc=0.01, flags=0, out_dtype=None):
 
 
 def _oracle(cfg, inp, tc=0.01):
-    if cfg.euclid or cfg.t2_dim():       # ablation blocks: the torch restatement (fp64) is the checker
-        from oracle import torch_port as tp
-        d = lambda t: t.double()
-        return tp.gta_attention(cfg, d(inp["q"]), d(inp["k"]), d(inp["v"]), d(inp["extr_q"]), d(inp["extr_k"]),
-                                d(inp["coord_q"]), d(inp["coord_k"]), trans_coeff=tc).float().numpy()
     from oracle import c_oracle
     return c_oracle.gta_attention(cfg, inp["q"].float(), inp["k"].float(), inp["v"].float(), inp["extr_q"],
                                   inp["extr_k"], inp["coord_q"], inp["coord_k"], trans_coeff=tc)

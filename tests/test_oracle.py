@@ -34,13 +34,15 @@ def test_torch_port_matches_golden(name):
     assert np.abs(out.numpy() - g["out"]).max() < 2e-6
 
 
-@pytest.mark.parametrize("name", [c[0] for c in CASES])
+@pytest.mark.parametrize("name", [c[0] for c in CASES + ABLATION_CASES])
 def test_c_oracle_matches_golden(name):
     cfg, cross = _case(name)
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     out = c_oracle.gta_attention(cfg, g["q"], g["k"], g["v"], g["extr_q"], g["extr_k"], g["coord_q"],
                                  g["coord_k"], trans_coeff=float(g["trans_coeff"]))
-    assert np.abs(out - g["out"]).max() < 5e-6
+    assert np.abs(out - g["out"]).max() < 5e-6 * max(1.0, float(np.abs(g["out"]).max()))
+    if cfg.t2_dim() or cfg.euclid:
+        return          # the packed rep tables below belong to the fused-path layouts
     r = c_oracle.build_reps(cfg, g["extr_q"], g["extr_k"], g["coord_q"], g["coord_k"])
     if "ref_se3rep_k" in g:
         assert np.abs(r["se3_k"].reshape(g["ref_se3rep_k"].shape) - g["ref_se3rep_k"]).max() < 1e-6
@@ -171,6 +173,9 @@ def test_ablation_blocks_against_live_reference(base, nq, nk, tq, tk, cross, vt)
     o2 = tp.gta_attention(cfg, inp["q"], inp["k"], inp["v"], inp["extr_q"], inp["extr_k"],
                           inp["coord_q"], inp["coord_k"], trans_coeff=0.3)
     assert (o2 - ref).abs().max() < 2e-6
+    o3 = c_oracle.gta_attention(cfg, inp["q"], inp["k"], inp["v"], inp["extr_q"], inp["extr_k"],
+                                inp["coord_q"], inp["coord_k"], trans_coeff=0.3)
+    assert np.abs(o3 - ref.numpy()).max() < 5e-6
     if cfg.t2_dim():
         assert (tp.t2_mats(inp["coord_k"]) - ex["t2rep_k"]).abs().max() == 0
 
