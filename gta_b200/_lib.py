@@ -53,6 +53,8 @@ SYMBOLS = {
     "gta_attn_fwd": (c_int, [POINTER(GtaAttnParams), c_void_p]),
     "gta_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "gta_attn_bwd": (c_int, [POINTER(GtaAttnBwdParams), c_void_p]),
+    "gta_attn_probs_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "gta_attn_probs": (c_int, [POINTER(GtaAttnParams), c_void_p, c_void_p]),
     "gta_rotate_debug": (c_int, [POINTER(GtaAttnParams), c_void_p, c_void_p, c_void_p, c_void_p]),
     "gta_build_reps": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_float, c_float, c_int, c_int] + [c_void_p] * 7),
     "gta_so2_mats": (c_int, [c_void_p, c_int64, c_int, c_float, c_float, c_int, c_void_p, c_void_p]),

@@ -30,6 +30,8 @@ int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st);
 bool attn_needs_generic(const GtaAttnParams& p);
 size_t generic_workspace_bytes(const GtaAttnParams& p);
 int launch_attn_fwd_generic(const GtaAttnParams& p, cudaStream_t st);
+size_t attn_probs_workspace_bytes(int B, int H, int Tq, int Tk, int D);
+int launch_attn_probs(const GtaAttnParams& p, float* attn, cudaStream_t st);
 int launch_rotate_debug_generic(const GtaAttnParams& p, float* qt, float* kt, float* vt, cudaStream_t st);
 
 int validate_attn_params(const GtaAttnParams* p);

@@ -109,6 +109,14 @@ int gta_attn_bwd(const GtaAttnBwdParams* p, void* stream) {
     return launch_attn_bwd(*p, static_cast<cudaStream_t>(stream));
 }
 
+size_t gta_attn_probs_workspace_bytes(int B, int H, int Tq, int Tk, int D) { return attn_probs_workspace_bytes(B, H, Tq, Tk, D); }
+
+int gta_attn_probs(const GtaAttnParams* p, float* attn, void* stream) {
+    int rc = validate_attn_params(p);
+    if (rc) return rc;
+    return launch_attn_probs(*p, attn, static_cast<cudaStream_t>(stream));
+}
+
 int gta_rotate_debug(const GtaAttnParams* p, float* qt, float* kt, float* vt, void* stream) {
     int rc = validate_attn_params(p);
     if (rc) return rc;

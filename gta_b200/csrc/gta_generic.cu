@@ -264,6 +264,46 @@ int launch_attn_fwd_generic(const GtaAttnParams& p, cudaStream_t st) {
     return check_launch("gta_attn_fwd (generic output rep)");
 }
 
+// attn[b,h,i,j] = exp(q'_i . k'_j * scale - lse[b,h,i]): 16x16 output tile per block, operands staged through shared memory.
+__global__ void attn_probs_kernel(const float* __restrict__ qt, const float* __restrict__ kt, const float* __restrict__ lse,
+                                  float* __restrict__ attn, int Tq, int Tk, int D, float scale) {
+    __shared__ float sq[16][129], sk[16][129];
+    const int bh = blockIdx.z, i0 = blockIdx.y * 16, j0 = blockIdx.x * 16;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float* qb = qt + static_cast<size_t>(bh) * Tq * D;
+    const float* kb = kt + static_cast<size_t>(bh) * Tk * D;
+    for (int idx = threadIdx.x; idx < 16 * D; idx += 256) {
+        const int r = idx / D, c = idx - r * D;
+        sq[r][c] = (i0 + r < Tq) ? qb[static_cast<size_t>(i0 + r) * D + c] : 0.f;
+        sk[r][c] = (j0 + r < Tk) ? kb[static_cast<size_t>(j0 + r) * D + c] : 0.f;
+    }
+    __syncthreads();
+    const int i = i0 + ty, j = j0 + tx;
+    if (i >= Tq || j >= Tk) return;
+    float dot = 0.f;
+    for (int c = 0; c < D; ++c) dot = fmaf(sq[ty][c], sk[tx][c], dot);
+    attn[(static_cast<size_t>(bh) * Tq + i) * Tk + j] = expf(dot * scale - lse[static_cast<size_t>(bh) * Tq + i]);
+}
+
+size_t attn_probs_workspace_bytes(int B, int H, int Tq, int Tk, int D) {
+    if (B <= 0 || H <= 0 || Tq <= 0 || Tk <= 0 || D <= 0) return 0;
+    return align_up(static_cast<size_t>(B) * H * Tq * D * 4) + align_up(static_cast<size_t>(B) * H * Tk * D * 4);
+}
+
+int launch_attn_probs(const GtaAttnParams& p, float* attn, cudaStream_t st) {
+    if (p.euclid) return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_probs: not defined for euclid_sim");
+    if (!p.lse || !attn) return set_error(GTA_ERR_INVALID, "gta_attn_probs: null lse / attn");
+    if (!p.workspace || p.workspace_bytes < attn_probs_workspace_bytes(p.B, p.H, p.Tq, p.Tk, p.D))
+        return set_error(GTA_ERR_INVALID, "gta_attn_probs: workspace too small");
+    float* qt = static_cast<float*>(p.workspace);
+    float* kt = reinterpret_cast<float*>(static_cast<uint8_t*>(p.workspace) + align_up(static_cast<size_t>(p.B) * p.H * p.Tq * p.D * 4));
+    int rc = launch_rotate_debug_generic(p, qt, kt, nullptr, st);      // dense fp32 q' = rho_q^{-T} q, k' = rho_k k
+    if (rc) return rc;
+    dim3 grid((p.Tk + 15) / 16, (p.Tq + 15) / 16, p.B * p.H);
+    attn_probs_kernel<<<grid, 256, 0, st>>>(qt, kt, p.lse, attn, p.Tq, p.Tk, p.D, p.scale);
+    return check_launch("gta_attn_probs");
+}
+
 // fp32 rotated operands [B,H,T,D] (no padding) for tests.
 int launch_rotate_debug_generic(const GtaAttnParams& p, float* qt, float* kt, float* vt, cudaStream_t st) {
     for (int which = 0; which < 3; ++which) {

@@ -25,6 +25,10 @@ from .ops import PackedReps
 from .synth import make_2dcoord  # noqa: F401  (same values as source/utils/gta.py:9-16)
 
 _original = None          # the reference implementation captured by install()
+# The reference returns the full [B,H,Tq,Tk] attention map as its second output; it is only read when a Transformer is
+# called with return_last_attmap=True (source/layers.py:478-480, heads == 1, off in every shipped config — SURVEY T7).
+# Set this to True to have the drop-in materialise it (gta_attn_probs); the default returns None in its place.
+RETURN_ATTENTION_MAP = False
 _PACK_KEY = "_gta_b200_packed"
 
 
@@ -155,6 +159,10 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
     if needs_grad:
         tc_param = tc if (tc is not None and torch.is_tensor(trans_coeff)) else tc
         return _FusedGtaAttention.apply(q, k, v, tc_param, packed, dict(f_dims), scale, bool(v_transform)), None
+    if RETURN_ATTENTION_MAP and not euclid:
+        out, lse = ops.gta_attention_fwd(q, k, v, packed, f_dims, trans_coeff=tc, scale=scale, v_transform=v_transform,
+                                         return_lse=True)
+        return out, ops.gta_attention_probs(q, k, lse, packed, f_dims, trans_coeff=tc, scale=scale)
     out = ops.gta_attention_fwd(q, k, v, packed, f_dims, trans_coeff=tc, scale=scale, v_transform=v_transform,
                                 euclid=euclid)
     return out, None

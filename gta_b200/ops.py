@@ -191,6 +191,28 @@ def gta_attention_bwd(dout: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: t
     return dq.permute(0, 2, 1, 3), dk.permute(0, 2, 1, 3), dv.permute(0, 2, 1, 3), dtc
 
 
+def gta_attention_probs(q: torch.Tensor, k: torch.Tensor, lse: torch.Tensor, reps: PackedReps, f_dims: dict, *,
+                        trans_coeff: Optional[torch.Tensor] = None, scale: Optional[float] = None) -> torch.Tensor:
+    """The attention map the reference returns next to `out` (source/layers.py:207-211): fp32 [B,H,Tq,Tk] from q, k and
+    the log-sum-exp of a forward call (`gta_attention_fwd(..., return_lse=True)`).  Visualisation path."""
+    B, H, Tq, D = q.shape
+    Tk = k.shape[2]
+    dev = q.device
+    if scale is None:
+        scale = D ** -0.5
+    if trans_coeff is not None:
+        trans_coeff = trans_coeff.detach().to(device=dev, dtype=torch.float32).reshape(-1)[:1].contiguous()
+    attn = torch.empty(B, H, Tq, Tk, device=dev, dtype=torch.float32)
+    dummy = torch.empty(16, device=dev, dtype=q.dtype)
+    p = _params(q, k, k, dummy, reps, f_dims, trans_coeff, scale, True, 0, lse.contiguous())
+    nbytes = lib().gta_attn_probs_workspace_bytes(B, H, Tq, Tk, D)
+    ws = _workspace(dev, nbytes)
+    p.workspace = (ws.data_ptr() + 1023) // 1024 * 1024
+    p.workspace_bytes = nbytes
+    check(lib().gta_attn_probs(p, _ptr(attn), _stream()), "gta_attn_probs")
+    return attn
+
+
 def rotate_debug(q, k, v, reps: PackedReps, f_dims: dict, *, trans_coeff=None, v_transform=True, euclid=False):
     """fp32 rotated operands (q', k', v') as contiguous [B,H,T,D] tensors — for tests."""
     dev = q.device

@@ -138,6 +138,14 @@ typedef struct GtaAttnBwdParams {
 size_t gta_attn_bwd_workspace_bytes(int B, int H, int Tq, int Tk, int D);
 int gta_attn_bwd(const GtaAttnBwdParams* p, void* stream);
 
+/* The attention map the reference returns as its second output (source/layers.py:207-211 `attn`, consumed only under
+ * return_last_attmap, source/layers.py:478-480 / SURVEY T7): attn[b,h,i,j] = exp(q'_i . k'_j * scale - lse[b,h,i]), fp32
+ * [B,H,Tq,Tk], from the same parameters as a previous gta_attn_fwd call whose p->lse was requested.  Materialises
+ * B*H*Tq*Tk floats — a visualisation path (fp32 SIMT dot products), not a hot path.  Not defined for euclid_sim.
+ * Workspace: gta_attn_probs_workspace_bytes (dense fp32 q', k'). */
+size_t gta_attn_probs_workspace_bytes(int B, int H, int Tq, int Tk, int D);
+int gta_attn_probs(const GtaAttnParams* p, float* attn, void* stream);
+
 /* Rotated operands only (q' = rho_q^{-T} q etc.), fp32 [B,H,T,D] contiguous; testing / inspection. */
 int gta_rotate_debug(const GtaAttnParams* p, float* qt, float* kt, float* vt, void* stream);
 

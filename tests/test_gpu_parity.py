@@ -518,3 +518,42 @@ def test_host_pipeline_matches_device_call():
         torch.cuda.synchronize()
         ref = _run(cfg, inp)                                  # [B,H,Tq,D]
         assert np.array_equal(out_host.permute(0, 2, 1, 3).float().numpy(), ref)
+
+
+@pytest.mark.parametrize("base", [MSN_SO3, CLEVR_T2], ids=["msn_so3", "clevr_t2"])
+def test_attention_map_output(base):
+    """The reference's second return value (`attn`, source/layers.py:207-211) through gta_attn_probs and
+    through the drop-in with RETURN_ATTENTION_MAP."""
+    from gta_b200 import gta as fast
+    from oracle import torch_port as tp
+    ops = _ops()
+    cfg = GtaConfig(**base, n_q_views=3, n_k_views=2)
+    inp = make_inputs(cfg, 2, 30, 45, cross=True, seed=61, dtype=torch.bfloat16)
+    reps = _dev_reps(cfg, inp)
+    q, k, v = (inp[n].cuda() for n in "qkv")
+    tc = torch.tensor([0.3], device="cuda")
+    out, lse = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True)
+    attn = ops.gta_attention_probs(q, k, lse, reps, cfg.f_dims, trans_coeff=tc).cpu()
+    r = tp.build_reps(cfg, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"])
+    qt, kt, vt = tp.transform_qkv(cfg, inp["q"].float(), inp["k"].float(), inp["v"].float(), r, 0.3)
+    ref = torch.softmax(qt @ kt.transpose(-1, -2) * cfg.head_dim ** -0.5, -1)
+    assert attn.shape == ref.shape
+    assert (attn - ref).abs().max() < 1e-2
+    assert (attn.sum(-1) - 1).abs().max() < 2e-2
+    # attn @ v' reproduces the forward output (before the output rep): consistency of the map with the fused kernel
+    if not cfg.t2_dim():
+        extras = {"se3rep_q": torch.linalg.inv(inp["extr_q"]).cuda(), "se3rep_k": r["se3_k"].cuda(), "inv_se3rep_q": r["se3_qinv"].cuda(),
+                  "so3rep_q": [r["so3_d1_q"].cuda(), r["so3_d2_q"].cuda()], "so3rep_k": [r["so3_d1_k"].cuda(), r["so3_d2_k"].cuda()],
+                  "so2rep_q": tp.so2_mats(r["so2_th_q"]).cuda(), "so2rep_k": tp.so2_mats(r["so2_th_k"]).cuda()}
+
+        class AttnFn:
+            scale = cfg.head_dim ** -0.5
+        fast.RETURN_ATTENTION_MAP = True
+        try:
+            with torch.no_grad():
+                o2, a2 = fast.multihead_geometric_transform_attention(q, k, v, AttnFn(), cfg.f_dims, extras, trans_coeff=tc)
+        finally:
+            fast.RETURN_ATTENTION_MAP = False
+        assert a2 is not None and (a2.cpu() - ref).abs().max() < 1e-2
+        # (the extras-based reps were built by torch on the host, `out` with the device rep builder: equal up to rounding)
+        assert (o2.float() - out.float()).abs().max() < 1e-2
