@@ -54,3 +54,17 @@ def test_two_rank_gloo():
     assert [r[1:3] for r in res] == [(0, 33), (33, 65)]
     assert all(r[3] == 15.0 and r[4] == 65 for r in res)
     assert job_throughput(1000, 2, 15.0) == 2000 / 0.015
+
+
+def test_packed_reps_batch_slice_is_a_view():
+    """Batch chunking of the host-buffer pipeline (gta_b200/host.py): the packed rep tables slice along the batch."""
+    import torch
+    from gta_b200.ops import PackedReps
+    r = PackedReps(se3_q=torch.arange(4 * 2 * 16.).reshape(4, 2, 16), se3_k=torch.zeros(4, 3, 16),
+                   so2_q=torch.ones(4, 10, 6, 2), n_q_views=2, n_k_views=3)
+    s = r.batch_slice(1, 3)
+    assert s.se3_q.shape == (2, 2, 16) and s.se3_q.data_ptr() == r.se3_q[1:3].data_ptr()
+    assert s.so3_q is None and s.so2_q.shape == (2, 10, 6, 2) and (s.n_q_views, s.n_k_views) == (2, 3)
+    B, chunks = 64, 16
+    bounds = [(B * i // chunks, B * (i + 1) // chunks) for i in range(chunks)]
+    assert bounds[0] == (0, 4) and bounds[-1] == (60, 64) and all(b[0] == a[1] for a, b in zip(bounds, bounds[1:]))
