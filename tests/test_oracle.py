@@ -204,3 +204,42 @@ def test_grad_oracle_matches_reference_autograd(base, nq, nk, tq, tk, cross):
         grads.append((q.grad, k.grad, v.grad, tc.grad))
     for a, b in zip(*grads):
         assert (a - b).abs().max() < 5e-6 * max(1.0, float(b.abs().max()))
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES + ABLATION_CASES])
+def test_dropin_packs_reference_format_reps(name):
+    """Host logic of the drop-in (gta_b200.gta._pack_reps): the rep tensors exactly as the reference's pre_compute_reps
+    left them in `extras` (stored in the golden files) are packed into the tables the CUDA library reads — checked
+    against the C oracle's tables built from the raw poses / coordinates."""
+    from gta_b200 import gta as fast
+    cfg, cross = _case(name)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    extras = {}
+    for key in ("se3rep_q", "se3rep_k", "inv_se3rep_q", "so2rep_q", "so2rep_k", "t2rep_q", "t2rep_k", "inv_t2rep_q"):
+        if "ref_" + key in g:
+            extras[key] = T(g["ref_" + key])
+    for side in ("q", "k"):
+        if f"ref_so3rep_{side}_d1" in g:
+            extras[f"so3rep_{side}"] = [T(g[f"ref_so3rep_{side}_d1"]), T(g[f"ref_so3rep_{side}_d2"])]
+    if not cross:       # self-attention: the reference stores the same objects under the _q and _k keys (encoder.py:196,213,235)
+        for key in ("so2rep", "t2rep"):
+            if key + "_q" in extras:
+                extras[key + "_k"] = extras[key + "_q"]
+    B = g["q"].shape[0]
+    p = fast._pack_reps(extras, cfg.f_dims, B, cfg.euclid)
+    r = c_oracle.build_reps(cfg, g["extr_q"], g["extr_k"], g["coord_q"], g["coord_k"])
+    triv, se3, so3, so2 = cfg.dims()
+    if se3:
+        assert np.abs(p.se3_q.numpy() - r["se3_q"]).max() < 1e-6 and np.abs(p.se3_k.numpy() - r["se3_k"]).max() < 1e-6
+        assert (p.n_q_views, p.n_k_views) == (cfg.n_q_views, cfg.n_k_views)
+        if cfg.euclid:
+            assert np.abs(p.se3_qi.numpy() - np.linalg.inv(g["extr_q"].astype(np.float64)).reshape(B, -1, 16)).max() < 1e-5
+    if so3:
+        assert np.abs(p.so3_q.numpy() - r["so3_q"]).max() < 2e-6 and np.abs(p.so3_k.numpy() - r["so3_k"]).max() < 2e-6
+    if so2:
+        assert np.abs(p.so2_q.numpy() - r["so2_q"]).max() < 2e-6 and np.abs(p.so2_k.numpy() - r["so2_k"]).max() < 2e-6
+        assert (p.so2_q is p.so2_k) == (not cross)
+    if cfg.t2_dim():
+        assert np.array_equal(p.t2_q.numpy(), g["coord_q"].reshape(B, -1, 2))
+        assert np.array_equal(p.t2_k.numpy(), g["coord_k"].reshape(B, -1, 2))
+    assert extras[fast._PACK_KEY][1] is p and fast._pack_reps(extras, cfg.f_dims, B, cfg.euclid) is p    # cached
