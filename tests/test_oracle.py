@@ -243,3 +243,36 @@ def test_dropin_packs_reference_format_reps(name):
         assert np.array_equal(p.t2_q.numpy(), g["coord_q"].reshape(B, -1, 2))
         assert np.array_equal(p.t2_k.numpy(), g["coord_k"].reshape(B, -1, 2))
     assert extras[fast._PACK_KEY][1] is p and fast._pack_reps(extras, cfg.f_dims, B, cfg.euclid) is p    # cached
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted (GPU box)")
+def test_install_rebinds_reference_globals_and_delegates_cpu_calls():
+    """gta_b200.gta.install(): source.layers resolves the operator by name at call time (layers.py:6,419), so rebinding
+    the module globals swaps the implementation; a CPU call is delegated to the captured reference function (same
+    result), and uninstall() restores the originals."""
+    import warnings
+    from gta_b200 import gta as fast
+    m = ref_harness.load()
+    import source.layers as rlayers
+    orig = m.gta.multihead_geometric_transform_attention
+    cfg = GtaConfig(**MSN_SO3, n_q_views=2, n_k_views=2)
+    inp = make_inputs(cfg, 1, 9, 9, cross=False, seed=3)
+    extras = ref_harness.ref_reps(cfg, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"], False)
+    fn = ref_harness._AttnFn(cfg.head_dim ** -0.5)
+    tc = torch.tensor([0.05])
+    ref, _ = orig(inp["q"], inp["k"], inp["v"], attn_fn=fn, f_dims=dict(cfg.f_dims), reps=extras, trans_coeff=tc)
+    try:
+        assert fast.install() is orig
+        assert rlayers.multihead_geometric_transform_attention is fast.multihead_geometric_transform_attention
+        assert m.gta.multihead_geometric_transform_attention is fast.multihead_geometric_transform_attention
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            out, attn = rlayers.multihead_geometric_transform_attention(
+                inp["q"], inp["k"], inp["v"], attn_fn=fn, f_dims=dict(cfg.f_dims), reps=extras, trans_coeff=tc)
+        assert any("delegating" in str(x.message) for x in w)
+        assert torch.equal(out, ref) and attn is not None
+    finally:
+        fast.uninstall()
+    assert rlayers.multihead_geometric_transform_attention is orig and m.gta.multihead_geometric_transform_attention is orig
+    with pytest.raises(NotImplementedError):      # without install() there is nothing to delegate to — and no CPU fallback
+        fast.multihead_geometric_transform_attention(inp["q"], inp["k"], inp["v"], fn, dict(cfg.f_dims), extras, trans_coeff=tc)
