@@ -45,6 +45,41 @@ def test_struct_layout_matches_header_order():
     assert order == names
 
 
+def _header_fields(struct):
+    txt = open(os.path.join(ROOT, "include", "gta_b200.h")).read()
+    body = txt[txt.index("typedef struct " + struct):txt.index("} " + struct + ";")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    order = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        decl = re.sub(r"^(const\s+)?(void|float|int64_t|int|size_t|GtaReps|GtaAttnParams|long long)\s*\*?\s*", "", decl)
+        order += [d.strip().lstrip("*") for d in decl.split(",")]
+    return order
+
+
+def test_reps_and_backward_struct_layouts_match_header_order():
+    assert _header_fields("GtaReps") == [f[0] for f in _lib.GtaReps._fields_]
+    assert _header_fields("GtaAttnBwdParams") == [f[0] for f in _lib.GtaAttnBwdParams._fields_]
+    assert ctypes.sizeof(_lib.GtaAttnBwdParams) == ctypes.sizeof(_lib.GtaAttnParams) + 7 * 8
+
+
+def test_backward_and_probs_argument_validation():
+    l = _lib.lib()
+    bp = _lib.GtaAttnBwdParams()
+    bp.fwd = _params()
+    assert l.gta_attn_bwd(ctypes.byref(bp), None) == -1 and "lse" in l.gta_last_error().decode()
+    bp.fwd = _params(se3=12, so3=8, so2=6, t2=6)
+    bp.fwd.reps = _lib.GtaReps(*([0x1000] * 6), None, 0x1000, 0x1000)
+    assert l.gta_attn_bwd(ctypes.byref(bp), None) == -3 and "no fused backward" in l.gta_last_error().decode()
+    assert l.gta_attn_bwd(None, None) == -1
+    assert l.gta_attn_bwd_workspace_bytes(1, 2, 16, 16, 32) == 2 * 2 * 8192 + 2 * 2 * 8192 + 1024
+    p = _params()
+    assert l.gta_attn_probs(ctypes.byref(p), None, None) == -1 and "lse" in l.gta_last_error().decode()
+    assert l.gta_attn_probs_workspace_bytes(1, 2, 16, 16, 32) == 2 * 4096
+
+
 def test_workspace_bytes():
     l = _lib.lib()
     # 2 tensors x B*H x ceil(Tk/128) tiles x 128*D*2 bytes
