@@ -11,8 +11,18 @@ from . import _lib
 from ._lib import GtaAttnBwdParams, GtaAttnParams, GtaReps, check, lib
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+FLAG_FAST_FP32 = _lib.GTA_FLAG_FAST_FP32
+
+
+def _stream(dev=None) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _launch(dev, name: str, *args) -> None:
+    """Every library call runs with the tensors' device current and on that device's current stream (the C ABI
+    launches on the calling thread's current device)."""
+    with torch.cuda.device(dev):
+        check(getattr(lib(), name)(*args, _stream(dev)), name)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -72,14 +82,14 @@ def build_reps(extr_q: torch.Tensor, extr_k: torch.Tensor, coord_q: torch.Tensor
     if so2_nfreqs:
         r.so2_k = f(B, Tk, 2 * so2_nfreqs, 2)
         r.so2_q = r.so2_k if same else f(B, Tq, 2 * so2_nfreqs, 2)
-    check(lib().gta_build_reps(_ptr(eq), _ptr(ek), _ptr(cq), _ptr(ck), B, Nq, Nk, Tq, Tk, int(so2_nfreqs),
+    _launch(dev, "gta_build_reps", _ptr(eq), _ptr(ek), _ptr(cq), _ptr(ck), B, Nq, Nk, Tq, Tk, int(so2_nfreqs),
                                float(max_freq_h), float(max_freq_w), int(shared_freqs), int(so3_maxdeg),
                                _ptr(r.se3_q), _ptr(r.se3_k), _ptr(r.so3_q), _ptr(r.so3_k), _ptr(r.so2_q),
-                               _ptr(r.so2_k), _stream()), "gta_build_reps")
+                               _ptr(r.so2_k))
     if euclid and se3:          # the euclid branch multiplies the query points by inv(E_q) itself (gta.py:140,153)
         r.se3_qi = r.se3_k if same else f(B, Nq, 16)
         if not same:
-            check(lib().gta_se3_inverse(_ptr(eq), B * Nq, _ptr(r.se3_qi), _stream()), "gta_se3_inverse")
+            _launch(dev, "gta_se3_inverse", _ptr(eq), B * Nq, _ptr(r.se3_qi))
     if t2:                      # make_T2mats needs nothing but the coordinates (gta.py:72-89)
         r.t2_q, r.t2_k = cq, ck
     return r
@@ -90,7 +100,9 @@ _ws_cache: Dict[tuple, torch.Tensor] = {}
 
 
 def _workspace(dev, nbytes: int) -> torch.Tensor:
-    key = (dev.index,)
+    """Scratch for the staged K'/V' tile images, one buffer per (device, stream): two streams running the op
+    concurrently never share staged tiles, and work queued on one stream reuses its buffer in stream order."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream(dev))
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(nbytes + 1024, device=dev, dtype=torch.uint8)
@@ -153,7 +165,7 @@ def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: P
     p.workspace = (base + 1023) // 1024 * 1024
     p.workspace_bytes = nbytes
     p.debug_clocks = _ptr(debug_clocks)
-    check(lib().gta_attn_fwd(p, _stream()), "gta_attn_fwd")
+    _launch(dev, "gta_attn_fwd", p)
     res = out.permute(0, 2, 1, 3)
     return (res, lse) if return_lse else res
 
@@ -187,7 +199,7 @@ def gta_attention_bwd(dout: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: t
     ws = _workspace(dev, nbytes)
     bp.workspace = (ws.data_ptr() + 1023) // 1024 * 1024
     bp.workspace_bytes = nbytes
-    check(lib().gta_attn_bwd(bp, _stream()), "gta_attn_bwd")
+    _launch(dev, "gta_attn_bwd", bp)
     return dq.permute(0, 2, 1, 3), dk.permute(0, 2, 1, 3), dv.permute(0, 2, 1, 3), dtc
 
 
@@ -209,7 +221,7 @@ def gta_attention_probs(q: torch.Tensor, k: torch.Tensor, lse: torch.Tensor, rep
     ws = _workspace(dev, nbytes)
     p.workspace = (ws.data_ptr() + 1023) // 1024 * 1024
     p.workspace_bytes = nbytes
-    check(lib().gta_attn_probs(p, _ptr(attn), _stream()), "gta_attn_probs")
+    _launch(dev, "gta_attn_probs", p, _ptr(attn))
     return attn
 
 
@@ -225,7 +237,7 @@ def rotate_debug(q, k, v, reps: PackedReps, f_dims: dict, *, trans_coeff=None, v
     vt = torch.empty(B, H, Tk, D, device=dev, dtype=torch.float32)
     dummy = torch.empty(16, device=dev, dtype=q.dtype)
     p = _params(q, k, v, dummy, reps, f_dims, trans_coeff, 1.0, v_transform, 0, euclid=euclid)
-    check(lib().gta_rotate_debug(p, _ptr(qt), _ptr(kt), _ptr(vt), _stream()), "gta_rotate_debug")
+    _launch(dev, "gta_rotate_debug", p, _ptr(qt), _ptr(kt), _ptr(vt))
     return qt, kt, vt
 
 
@@ -234,8 +246,8 @@ def so2_mats(coord: torch.Tensor, nfreqs: int, max_freqs=(1, 1), shared_freqs: b
     assert coord.is_cuda and coord.shape[-1] == 2
     c = _f32c(coord).reshape(-1, 2)
     out = torch.empty(c.shape[0], 2 * nfreqs, 2, 2, device=c.device, dtype=torch.float32)
-    check(lib().gta_so2_mats(_ptr(c), c.shape[0], int(nfreqs), float(max_freqs[0]), float(max_freqs[1]),
-                             int(shared_freqs), _ptr(out), _stream()), "gta_so2_mats")
+    _launch(c.device, "gta_so2_mats", _ptr(c), c.shape[0], int(nfreqs), float(max_freqs[0]), float(max_freqs[1]),
+                             int(shared_freqs), _ptr(out))
     return out.reshape(*coord.shape[:-1], 2 * nfreqs, 2, 2)
 
 
@@ -246,7 +258,7 @@ def t2_mats(coord: torch.Tensor, with_inverse: bool = False):
     c = _f32c(coord).reshape(-1, 2)
     m = torch.empty(c.shape[0], 3, 3, device=c.device, dtype=torch.float32)
     mi = torch.empty_like(m) if with_inverse else None
-    check(lib().gta_t2_mats(_ptr(c), c.shape[0], _ptr(m), _ptr(mi), _stream()), "gta_t2_mats")
+    _launch(c.device, "gta_t2_mats", _ptr(c), c.shape[0], _ptr(m), _ptr(mi))
     m = m.reshape(*coord.shape[:-1], 3, 3)
     return (m, mi.reshape(*coord.shape[:-1], 3, 3)) if with_inverse else m
 
@@ -256,7 +268,7 @@ def se3_inverse(extr: torch.Tensor) -> torch.Tensor:
     assert extr.is_cuda and extr.shape[-2:] == (4, 4)
     e = _f32c(extr).reshape(-1, 16)
     out = torch.empty_like(e)
-    check(lib().gta_se3_inverse(_ptr(e), e.shape[0], _ptr(out), _stream()), "gta_se3_inverse")
+    _launch(e.device, "gta_se3_inverse", _ptr(e), e.shape[0], _ptr(out))
     return out.reshape(extr.shape)
 
 
@@ -266,7 +278,7 @@ def wigner_d(R: torch.Tensor):
     r = _f32c(R).reshape(-1, 3, 3)
     d1 = torch.empty(r.shape[0], 3, 3, device=r.device, dtype=torch.float32)
     d2 = torch.empty(r.shape[0], 5, 5, device=r.device, dtype=torch.float32)
-    check(lib().gta_wigner_d(_ptr(r), r.shape[0], _ptr(d1), _ptr(d2), _stream()), "gta_wigner_d")
+    _launch(r.device, "gta_wigner_d", _ptr(r), r.shape[0], _ptr(d1), _ptr(d2))
     return d1, d2
 
 
@@ -274,6 +286,5 @@ def umma_probe(A, Bm, P, V, p_in_tmem: bool):
     D = A.shape[1]
     outS = torch.empty(128, 128, device=A.device, dtype=torch.float32)
     outO = torch.empty(128, D, device=A.device, dtype=torch.float32)
-    check(lib().gta_umma_probe(_ptr(A), _ptr(Bm), _ptr(P), _ptr(V), D, int(p_in_tmem), _ptr(outS), _ptr(outO),
-                               _stream()), "gta_umma_probe")
+    _launch(A.device, "gta_umma_probe", _ptr(A), _ptr(Bm), _ptr(P), _ptr(V), D, int(p_in_tmem), _ptr(outS), _ptr(outO))
     return outS, outO
