@@ -41,6 +41,7 @@ int launch_rotate_debug(const GtaAttnParams& p, float* qt, float* kt, float* vt,
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v2(const GtaAttnParams& p, cudaStream_t st);
+int launch_attn_fwd_v3(const GtaAttnParams& p, bool fused, cudaStream_t st);
 int launch_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
                          cudaStream_t st);
 int launch_umma_bench(int D, int mode, int reps, int grid, long long* out, cudaStream_t st);
@@ -57,5 +58,13 @@ int launch_attn_fwd_hp(const GtaAttnParams& p, cudaStream_t st);
 // Scratch layout: [K' tiles | V' tiles], each tile image = D/32 column blocks x 128 rows x 64 B (bf16).
 inline int num_kv_tiles(int Tk) { return (Tk + 127) / 128; }
 inline size_t kv_tile_bytes(int D) { return static_cast<size_t>(128) * D * 2; }
+// The fused single-launch kernel keeps one ready flag (int) per (batch, head, key tile) behind the tile images.
+inline size_t kv_flags_offset(int B, int H, int Tk, int D) { return 2 * static_cast<size_t>(B) * H * num_kv_tiles(Tk) * kv_tile_bytes(D); }
+inline size_t kv_flags_bytes(int B, int H, int Tk) { return (static_cast<size_t>(B) * H * num_kv_tiles(Tk) * sizeof(int) + 1023) / 1024 * 1024; }
+// Which parameter sets the fused single-launch kernel (gta_attn_fwd4.cu) serves.
+inline bool attn_is_fused_launch(const GtaAttnParams& p) {
+    return !attn_is_split_precision(p) && p.D <= 96 &&
+           !(p.flags & (GTA_FLAG_SKIP_STAGE | GTA_FLAG_STAGE_ONLY | GTA_FLAG_V0_PIPELINE | GTA_FLAG_V1_PIPELINE | GTA_FLAG_TWO_LAUNCH));
+}
 
 }  // namespace gta

@@ -64,16 +64,17 @@ using namespace gta;
 extern "C" {
 
 const char* gta_last_error(void) { return g_err; }
-int gta_abi_version(void) { return 2; }
+int gta_abi_version(void) { return 3; }
 
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D) {
     if (B <= 0 || H <= 0 || Tk <= 0 || D <= 0) return 0;
-    return 2 * static_cast<size_t>(B) * H * num_kv_tiles(Tk) * kv_tile_bytes(D);
+    return kv_flags_offset(B, H, Tk, D) + kv_flags_bytes(B, H, Tk);
 }
 
 size_t gta_attn_fwd_workspace_bytes_ex(int B, int H, int Tk, int D, int in_dtype, int flags) {
-    const size_t base = gta_attn_fwd_workspace_bytes(B, H, Tk, D);
-    return (in_dtype == GTA_DTYPE_F32 && !(flags & GTA_FLAG_FAST_FP32)) ? 2 * base : base;
+    if (B <= 0 || H <= 0 || Tk <= 0 || D <= 0) return 0;
+    const size_t tiles = kv_flags_offset(B, H, Tk, D);
+    return ((in_dtype == GTA_DTYPE_F32 && !(flags & GTA_FLAG_FAST_FP32)) ? 2 * tiles : tiles) + kv_flags_bytes(B, H, Tk);
 }
 
 size_t gta_attn_fwd_workspace_bytes_p(const GtaAttnParams* p) {
@@ -91,6 +92,9 @@ int gta_attn_fwd(const GtaAttnParams* p, void* stream) {
     if (reinterpret_cast<uintptr_t>(p->workspace) & 1023) return set_error(GTA_ERR_INVALID, "workspace must be 1024-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (attn_needs_generic(*p)) return launch_attn_fwd_generic(*p, st);
+    if (attn_is_fused_launch(*p)) return launch_attn_fwd_v3(*p, true, st);           // one launch: rotation + attention
+    if ((p->flags & GTA_FLAG_SKIP_STAGE) && (p->flags & GTA_FLAG_V3_PRESTAGED) && !attn_is_split_precision(*p) && p->D <= 96)
+        return launch_attn_fwd_v3(*p, false, st);
     if (!(p->flags & GTA_FLAG_SKIP_STAGE)) {
         rc = launch_rotate_kv(*p, st);
         if (rc) return rc;

@@ -239,6 +239,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// Bulk prefetch of `bytes` contiguous bytes into L2 (size % 16 == 0, 16-byte aligned address); asynchronous, no completion.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ void prefetch_l1(const void* p) {
     asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
 }

@@ -120,6 +120,50 @@ __device__ __forceinline__ void apply_rep_chunk(float* x, int c, const HeadDims&
     }
 }
 
+// Same as apply_rep_chunk for TWO operands that share their rep data (chunk c of K and of V of one token, or of Q and dO):
+// the view matrix / token angles are loaded once.  `rot_b` = false leaves xb untouched (v_transform = False).
+template <int kMode>
+__device__ __forceinline__ void apply_rep_chunk_pair(float* xa, float* xb, bool rot_b, int c, const HeadDims& hd,
+                                                     const float* __restrict__ se3m, const float* __restrict__ so3m,
+                                                     const float* __restrict__ so2cs, float tc) {
+    const int e = c * 8;
+    if (e < hd.triv) return;
+    constexpr bool kT = (kMode == kModeQ || kMode == kModeKVT);        // se3: transposed matrix
+    constexpr bool kInv = (kMode == kModeOut || kMode == kModeKVT);    // so3 / so2: transposed (= inverse)
+    if (e < hd.triv + hd.se3) {
+        float M[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float4 r = __ldg(reinterpret_cast<const float4*>(se3m) + i);
+            M[4 * i] = r.x; M[4 * i + 1] = r.y; M[4 * i + 2] = r.z; M[4 * i + 3] = r.w;
+        }
+        if (kT) { se3_apply_T(xa, M, tc); if (rot_b) se3_apply_T(xb, M, tc); }
+        else { se3_apply(xa, M, tc); if (rot_b) se3_apply(xb, M, tc); }
+        return;
+    }
+    if (e < hd.triv + hd.se3 + hd.so3) {
+        float W[34];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            float2 r = __ldg(reinterpret_cast<const float2*>(so3m) + i);
+            W[2 * i] = r.x; W[2 * i + 1] = r.y;
+        }
+        so3_apply<kInv>(xa, W);
+        if (rot_b) so3_apply<kInv>(xb, W);
+        return;
+    }
+    {
+        const int pc = (e - hd.triv - hd.se3 - hd.so3) >> 1;
+        float cs[8];
+        float4 r0 = __ldg(reinterpret_cast<const float4*>(so2cs + 2 * pc));
+        float4 r1 = __ldg(reinterpret_cast<const float4*>(so2cs + 2 * pc) + 1);
+        cs[0] = r0.x; cs[1] = r0.y; cs[2] = r0.z; cs[3] = r0.w;
+        cs[4] = r1.x; cs[5] = r1.y; cs[6] = r1.z; cs[7] = r1.w;
+        so2_apply<kInv>(xa, cs);
+        if (rot_b) so2_apply<kInv>(xb, cs);
+    }
+}
+
 // 8 consecutive elements of a row -> fp32 registers (bf16 or fp32 source; 16-byte / 32-byte aligned).
 template <typename T>
 __device__ __forceinline__ void load_chunk(const T* __restrict__ p, float* x);
@@ -227,6 +271,130 @@ __device__ __forceinline__ void raw_to_f32(const RawChunk<__nv_bfloat16>& r, flo
 }
 __device__ __forceinline__ void raw_to_f32(const RawChunk<float>& r, float* x) {
     x[0] = r.a.x; x[1] = r.a.y; x[2] = r.a.z; x[3] = r.a.w; x[4] = r.b.x; x[5] = r.b.y; x[6] = r.b.z; x[7] = r.b.w;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// One whole head row (thread = token), walked block type by block type in batches of kB 16-byte chunks.  Everything a
+// batch needs (raw chunks of operand a and, with kPair, of operand b that shares its rep data; the view matrix of the
+// block type or the token's angles) is requested before the first use, so a row costs one memory round trip per batch
+// instead of one per chunk — the staging warps of the fused attention kernel have no other warps to hide latency behind.
+//   store(c, xa, xb): called once per chunk c in [0, D/8) with the transformed values (xb only meaningful with kPair).
+// `valid` = false writes zeros (rows past the end of the sequence).  `rot_b` = false leaves operand b untransformed.
+// (Measured alternatives that were slower in the fused kernel, see DESIGN.md: per-chunk rep loads, 32-byte paired
+// accesses with a generic segment walker, lanes along the row with per-item rep loads.)
+template <typename TIn, int kMode, bool kPair, int kB, typename Store>
+__device__ __forceinline__ void stage_row(const TIn* __restrict__ arow, const TIn* __restrict__ brow, const bool valid,
+                                          const bool rot_b, const HeadDims& hd, const float* __restrict__ se3m,
+                                          const float* __restrict__ so3m, const float* __restrict__ so2cs, const float tc,
+                                          Store&& store) {
+    constexpr bool kT = (kMode == kModeQ || kMode == kModeKVT);        // se3: transposed matrix
+    constexpr bool kInv = (kMode == kModeOut || kMode == kModeKVT);    // so3 / so2: transposed (= inverse)
+    const int c1 = hd.triv >> 3, c2 = c1 + (hd.se3 >> 3), c3 = c2 + (hd.so3 >> 3), c4 = c3 + (hd.so2 >> 3);
+    RawChunk<TIn> ra[kB], rb[kPair ? kB : 1];
+    auto load_batch = [&](int c0, int cend) {
+#pragma unroll
+        for (int i = 0; i < kB; ++i) {
+            zero_raw(ra[i]);
+            if (kPair) zero_raw(rb[i]);
+            if (valid && c0 + i < cend) {
+                load_raw(arow + (c0 + i) * 8, ra[i]);
+                if (kPair) load_raw(brow + (c0 + i) * 8, rb[i]);
+            }
+        }
+    };
+    // ---- trivial block: pass-through
+#pragma unroll 1
+    for (int c0 = 0; c0 < c1; c0 += kB) {
+        load_batch(c0, c1);
+#pragma unroll
+        for (int i = 0; i < kB; ++i) {
+            if (c0 + i < c1) {
+                float xa[8], xb[8];
+                raw_to_f32(ra[i], xa);
+                if (kPair) raw_to_f32(rb[i], xb);
+                store(c0 + i, xa, xb);
+            }
+        }
+    }
+    // ---- SE(3): two 4-vectors per chunk, one 4x4 per view
+    if (c2 > c1) {
+        float M[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(se3m) + i);
+            M[4 * i] = r.x; M[4 * i + 1] = r.y; M[4 * i + 2] = r.z; M[4 * i + 3] = r.w;
+        }
+#pragma unroll 1
+        for (int c0 = c1; c0 < c2; c0 += kB) {
+            load_batch(c0, c2);
+#pragma unroll
+            for (int i = 0; i < kB; ++i) {
+                if (c0 + i < c2) {
+                    float xa[8], xb[8];
+                    raw_to_f32(ra[i], xa);
+                    if (kPair) raw_to_f32(rb[i], xb);
+                    if (valid) {
+                        if (kT) se3_apply_T(xa, M, tc); else se3_apply(xa, M, tc);
+                        if (kPair && rot_b) { if (kT) se3_apply_T(xb, M, tc); else se3_apply(xb, M, tc); }
+                    }
+                    store(c0 + i, xa, xb);
+                }
+            }
+        }
+    }
+    // ---- SO(3): [3 | 5] per chunk, Wigner D_1 | D_2 per view
+    if (c3 > c2) {
+        float W[34];
+#pragma unroll
+        for (int i = 0; i < 17; ++i) {
+            const float2 r = __ldg(reinterpret_cast<const float2*>(so3m) + i);
+            W[2 * i] = r.x; W[2 * i + 1] = r.y;
+        }
+#pragma unroll 1
+        for (int c0 = c2; c0 < c3; c0 += kB) {
+            load_batch(c0, c3);
+#pragma unroll
+            for (int i = 0; i < kB; ++i) {
+                if (c0 + i < c3) {
+                    float xa[8], xb[8];
+                    raw_to_f32(ra[i], xa);
+                    if (kPair) raw_to_f32(rb[i], xb);
+                    if (valid) {
+                        so3_apply<kInv>(xa, W);
+                        if (kPair && rot_b) so3_apply<kInv>(xb, W);
+                    }
+                    store(c0 + i, xa, xb);
+                }
+            }
+        }
+    }
+    // ---- SO(2): four pairs per chunk, the token's (cos, sin) table
+#pragma unroll 1
+    for (int c0 = c3; c0 < c4; c0 += kB) {
+        So2Chunk cs[kB];
+#pragma unroll
+        for (int i = 0; i < kB; ++i) {
+            cs[i].a = make_float4(1.f, 0.f, 1.f, 0.f); cs[i].b = cs[i].a;
+            if (valid && c0 + i < c4) {
+                const float4* p4 = reinterpret_cast<const float4*>(so2cs + (c0 + i - c3) * 8);
+                cs[i].a = __ldg(p4); cs[i].b = __ldg(p4 + 1);
+            }
+        }
+        load_batch(c0, c4);
+#pragma unroll
+        for (int i = 0; i < kB; ++i) {
+            if (c0 + i < c4) {
+                float xa[8], xb[8];
+                raw_to_f32(ra[i], xa);
+                if (kPair) raw_to_f32(rb[i], xb);
+                const float c8[8] = {cs[i].a.x, cs[i].a.y, cs[i].a.z, cs[i].a.w, cs[i].b.x, cs[i].b.y, cs[i].b.z, cs[i].b.w};
+                so2_apply<kInv>(xa, c8);
+                if (kPair && rot_b) so2_apply<kInv>(xb, c8);
+                store(c0 + i, xa, xb);
+            }
+        }
+    }
 }
 
 }  // namespace gta

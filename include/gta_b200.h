@@ -102,8 +102,14 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_FAST_FP32 128 /* fp32 inputs: multiply in plain bf16 (1e-2 budget) instead of the split-precision path */
 #define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 #define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
+#define GTA_FLAG_TWO_LAUNCH 32  /* previous default, kept for A/B measurement: K'/V' staging kernel + persistent attention kernel
+                                   (two launches).  Without it bf16 / fast-fp32 calls with D <= 96 run ONE launch: the K/V
+                                   rotation is done by staging warps of the attention kernel itself (gta_attn_fwd4.cu) */
+#define GTA_FLAG_V3_PRESTAGED 64 /* with GTA_FLAG_SKIP_STAGE: run the single-launch kernel on an already staged workspace
+                                   (its rotation warps idle) instead of the two-launch attention kernel */
 
-/* Scratch for the rotated K'/V' operand tiles (bf16 inputs, or fp32 inputs with GTA_FLAG_FAST_FP32). */
+/* Scratch for the rotated K'/V' operand tiles (bf16 inputs, or fp32 inputs with GTA_FLAG_FAST_FP32) and the per-tile
+ * ready flags of the single-launch kernel. */
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D);
 /* Same for any dtype/flags: fp32 inputs use split-precision (hi + residual) tile images, twice the size. */
 size_t gta_attn_fwd_workspace_bytes_ex(int B, int H, int Tk, int D, int in_dtype, int flags);

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     l = _lib.lib()
     for name in _declared_symbols():
         assert hasattr(l, name), name
-    assert l.gta_abi_version() == 2
+    assert l.gta_abi_version() == 3
 
 
 def test_struct_layout_matches_header_order():

@@ -21,8 +21,9 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 BF16_TOL = 1e-2
 FP32_TOL = 1e-3
-# GTA_FLAG_* pipeline selectors of the product library: default persistent pipeline, V1 (non-persistent two-tile)
-PIPELINES, PIPELINE_IDS = [0, 16], ["v2", "v1"]
+# GTA_FLAG_* pipeline selectors of the product library: default single-launch pipeline (K/V rotation inside the attention
+# kernel), the two-launch pipeline (staging kernel + persistent attention kernel), V1 (non-persistent two-tile)
+PIPELINES, PIPELINE_IDS = [0, 32, 16], ["v3_fused", "v2_two_launch", "v1"]
 
 
 def _ops():
@@ -64,9 +65,11 @@ def _tol(ref, tc=0.01, base=BF16_TOL):
     return base * max(1.0, float(np.abs(ref).max())) * (2.0 if base == BF16_TOL else 1.0)
 
 
-def _check(out, ref, tc=0.01, base=BF16_TOL, what=""):
+def _check(out, ref, tc=0.01, base=BF16_TOL, what="", rel=False):
+    """rel=True: bound relative to max(1, |ref|_max) without the trans_coeff doubling (outputs well above 1, where the
+    bf16 rounding of the OUTPUT alone is |out| * 2^-9)."""
     err = float(np.abs(out - ref).max())
-    tol = _tol(ref, tc, base)
+    tol = base * max(1.0, float(np.abs(ref).max())) if rel else _tol(ref, tc, base)
     print("%s max-abs err %.3e (bound %.1e%s, |ref|max %.2f)" % (what, err, tol, "" if tc < 0.5 else " relative, tc=%g" % tc,
                                                               float(np.abs(ref).max())))
     assert np.isfinite(out).all()
@@ -159,7 +162,10 @@ def test_golden_vectors_ablation_blocks(name, dtype):
     out = _run(cfg, inp, tc=float(g["trans_coeff"]))
     # fp32 inputs run the split-precision path (fp32 budget) unless the padded head dim of euclid_sim exceeds 96
     hp = dtype == torch.float32 and cfg.head_dim + (32 if cfg.euclid else 0) <= 96
-    _check(out, ref, float(g["trans_coeff"]), FP32_TOL if hp else BF16_TOL, name)
+    # euclid_sim logits carry the -|k'|^2/2 terms (tens of units, not O(1)): their bf16 products set the error, so the
+    # bf16-math bound of that ablation is relative to |ref|_max like the trans_coeff >= 0.5 cases
+    tc_eff = 1.0 if (cfg.euclid and not hp) else float(g["trans_coeff"])
+    _check(out, ref, tc_eff, FP32_TOL if hp else BF16_TOL, name)
 
 
 def _golden_case(name):
@@ -304,7 +310,7 @@ def test_frame_invariance_and_linearity_full_size():
     assert np.abs(_run(cfg, inp3, out_dtype=torch.float32) - 2 * base).max() < 1e-5
 
 
-@pytest.mark.parametrize("flags", [0, 16], ids=["v2", "v1"])
+@pytest.mark.parametrize("flags", PIPELINES, ids=PIPELINE_IDS)
 @pytest.mark.parametrize("case", [(CLEVR, 2, 2, 300, 300, False, 32), (MSN_SO3, 5, 5, 256, 256, False, 24),
                                   (CLEVR, 3, 2, 853, 300, True, 8)],
                          ids=["clevr_enc_B32", "msn_enc_B24", "clevr_dec_B8"])
@@ -349,13 +355,26 @@ def test_sweep_length_row_subset():
     ref = c_oracle.gta_attention(cfg, inp["q"][:, :, rows].float(), inp["k"].float(), inp["v"].float(), inp["extr_k"],
                                  inp["extr_k"], inp["coord_k"][:, rows], inp["coord_k"], trans_coeff=0.01)
     _check(out[:, :, rows.numpy()], ref, what="L=32768 row subset")
-    # peaked rows: scaled queries make the running maximum jump by more than the lazy-rescale threshold between tiles
+    # peaked rows: scaled queries make the running maximum jump by more than the lazy-rescale threshold (2^8) between key
+    # tiles.  With logits of ~+-30 the bf16 rounding of the rotated OPERANDS alone moves a peaked softmax by several
+    # 1e-2 (inherent to bf16 inputs of a tensor-core product, kernel-independent), so the kernel is checked against the
+    # oracle evaluated on operands rounded exactly as the kernel rounds them (q', k', v' -> bf16), at the bf16 bound;
+    # the distance to the unrounded oracle is printed for reference.
+    from oracle import torch_port as tp
     inp2 = dict(inp)
     inp2["q"] = (inp["q"].float() * 8.0).to(torch.bfloat16)
-    out2 = _run(cfg, inp2)
-    ref2 = c_oracle.gta_attention(cfg, inp2["q"][:, :, rows].float(), inp["k"].float(), inp["v"].float(), inp["extr_k"],
-                                  inp["extr_k"], inp["coord_k"][:, rows], inp["coord_k"], trans_coeff=0.01)
-    _check(out2[:, :, rows.numpy()], ref2, what="L=32768 row subset, peaked")
+    out2 = _run(cfg, inp2)[:, :, rows.numpy()]
+    r = tp.build_reps(cfg, inp["extr_k"], inp["extr_k"], inp["coord_k"][:, rows], inp["coord_k"])
+    qt, kt, vt = tp.transform_qkv(cfg, inp2["q"][:, :, rows].float(), inp["k"].float(), inp["v"].float(), r, 0.01)
+    rb = lambda t: t.to(torch.bfloat16).double()
+    o = torch.softmax(rb(qt) @ rb(kt).transpose(-1, -2) * cfg.head_dim ** -0.5, -1) @ rb(vt)
+    T = lambda n: r[n].double().transpose(-1, -2)
+    ref2 = tp._apply_blocks(o, cfg, tp._scale_translation(r["se3_qinv"].double(), 0.01), T("so3_d1_q"), T("so3_d2_q"),
+                            r["so2_th_q"].double(), True, cfg.n_q_views).float().numpy()
+    _check(out2, ref2, what="L=32768 row subset, peaked (|out| up to ~4), vs oracle on bf16-rounded operands", rel=True)
+    exact = c_oracle.gta_attention(cfg, inp2["q"][:, :, rows].float(), inp["k"].float(), inp["v"].float(), inp["extr_k"],
+                                   inp["extr_k"], inp["coord_k"][:, rows], inp["coord_k"], trans_coeff=0.01)
+    print("  (vs the unrounded oracle: %.3e, |ref|max %.2f)" % (float(np.abs(out2 - exact).max()), float(np.abs(exact).max())))
 
 
 def test_msn_headline_batch_subset():

@@ -29,10 +29,13 @@ def main():
     flags = int(os.environ.get('GTA_FLAGS', '0'))
     for _ in range(3):
         ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, v_transform=cfg.v_transform, flags=int(os.environ.get('GTA_FLAGS', '0')))
-    dbg = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(2 * 148, 16, dtype=torch.int64, device=dev)     # [softmax/issuer plane | staging-warp plane]
     ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, v_transform=cfg.v_transform, debug_clocks=dbg, flags=int(os.environ.get('GTA_FLAGS', '0')))
     torch.cuda.synchronize()
-    d = dbg.cpu().double()
+    d_all = dbg.cpu().double()
+    grid_n = int((d_all[:148, 5] > 0).sum())
+    sd = d_all[grid_n:2 * grid_n]
+    d = d_all[:148]
     d = d[d[:, 5] > 0]
     items = d[:, 5]
     ntile = (nk * tk + 127) // 128
@@ -47,6 +50,11 @@ def main():
             print(f"  epilogue part {nme:30s} per item {(d[:,i]/items).mean():7.0f} clk")
     for i, nme in ((8, "k_full"), (9, "v_full"), (10, "p_full"), (11, "o_free"), (12, "q_full")):
         print(f"  UMMA issuer wait on {nme:7s} per item {(d[:,i]/items).mean():8.0f} clk ({100*(d[:,i]/d[:,0]).mean():5.1f}% of span)")
+    if sd[:, 0].sum() > 0:
+        it = items.mean()
+        print(f"  staging warps: span {sd[:,0].mean():.0f} clk; per item: K'/V' units {(sd[:,1]).mean()/it:.0f} clk "
+              f"({sd[:,3].mean()/it:.2f} units, {(sd[:,1]/sd[:,3].clamp(min=1)).mean():.0f} clk each), unit barrier {(sd[:,2]).mean()/it:.0f}, "
+              f"Q' staging {(sd[:,4]).mean()/it:.0f}, q_free wait {(sd[:,5]).mean()/it:.0f}")
 
 
 if __name__ == "__main__":
