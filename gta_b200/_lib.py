@@ -22,6 +22,7 @@ GTA_FLAG_FAST_FP32 = 128
 GTA_FLAG_V1_PIPELINE = 16
 GTA_FLAG_TWO_LAUNCH = 32
 GTA_FLAG_V3_PRESTAGED = 64
+GTA_FLAG_V4_PIPELINE = 256
 
 
 class GtaReps(ctypes.Structure):

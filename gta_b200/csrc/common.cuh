@@ -42,6 +42,7 @@ int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v2(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v3(const GtaAttnParams& p, bool fused, cudaStream_t st);
+int launch_attn_fwd_v4(const GtaAttnParams& p, cudaStream_t st, bool* handled);
 int launch_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
                          cudaStream_t st);
 int launch_umma_bench(int D, int mode, int reps, int grid, long long* out, cudaStream_t st);
@@ -64,7 +65,7 @@ inline size_t kv_flags_bytes(int B, int H, int Tk) { return (static_cast<size_t>
 // Which parameter sets the fused single-launch kernel (gta_attn_fwd4.cu) serves.
 inline bool attn_is_fused_launch(const GtaAttnParams& p) {
     return !attn_is_split_precision(p) && p.D <= 96 &&
-           !(p.flags & (GTA_FLAG_SKIP_STAGE | GTA_FLAG_STAGE_ONLY | GTA_FLAG_V0_PIPELINE | GTA_FLAG_V1_PIPELINE | GTA_FLAG_TWO_LAUNCH));
+           !(p.flags & (GTA_FLAG_SKIP_STAGE | GTA_FLAG_STAGE_ONLY | GTA_FLAG_V0_PIPELINE | GTA_FLAG_V1_PIPELINE | GTA_FLAG_TWO_LAUNCH | GTA_FLAG_V4_PIPELINE));
 }
 
 }  // namespace gta

@@ -373,7 +373,14 @@ static int launch2_d(const AttnArgs& a, int D, dim3 grid, cudaStream_t st) {
 
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st) {
     if (p.flags & GTA_FLAG_V0_PIPELINE) return launch_attn_fwd_v0(p, st);
-    if (!(p.flags & GTA_FLAG_V1_PIPELINE) && p.D <= 96) return launch_attn_fwd_v2(p, st);  // default: persistent pipeline
+    if (!(p.flags & GTA_FLAG_V1_PIPELINE) && p.D <= 96) {
+        if (p.flags & GTA_FLAG_V4_PIPELINE) {
+            bool handled = false;
+            const int rc = launch_attn_fwd_v4(p, st, &handled);
+            if (handled) return rc;
+        }
+        return launch_attn_fwd_v2(p, st);  // persistent pipeline
+    }
     const AttnArgs a = make_attn_args(p);
     dim3 grid((p.Tq + 255) / 256, p.H, p.B);
     const bool ib = p.in_dtype == GTA_DTYPE_BF16, ob = p.out_dtype == GTA_DTYPE_BF16;

@@ -769,6 +769,7 @@ int launch_attn_fwd_v3(const GtaAttnParams& p, bool fused, cudaStream_t st) {
     Fused4Args f;
     f.rot = make_rot_args_kv(p);
     f.nunits = p.B * p.H * a.ntiles_k;
+    f.flags = fused ? reinterpret_cast<int*>(static_cast<uint8_t*>(p.workspace) + kv_flags_offset(p.B, p.H, p.Tk, p.D)) : nullptr;
     const bool ib = p.in_dtype == GTA_DTYPE_BF16, ob = p.out_dtype == GTA_DTYPE_BF16;
     if (ib && ob) return launch4_d<__nv_bfloat16, __nv_bfloat16>(a, f, p, st);
     if (ib && !ob) return launch4_d<__nv_bfloat16, float>(a, f, p, st);

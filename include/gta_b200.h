@@ -105,6 +105,8 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_TWO_LAUNCH 32  /* previous default, kept for A/B measurement: K'/V' staging kernel + persistent attention kernel
                                    (two launches).  Without it bf16 / fast-fp32 calls with D <= 96 run ONE launch: the K/V
                                    rotation is done by staging warps of the attention kernel itself (gta_attn_fwd4.cu) */
+#define GTA_FLAG_V4_PIPELINE 256 /* two launches with the streaming-softmax / epilogue-warpgroup attention kernel (gta_attn_fwd5.cuh);
+                                    head layouts without an instantiation fall back to the gta_attn_fwd3.cu kernel */
 #define GTA_FLAG_V3_PRESTAGED 64 /* with GTA_FLAG_SKIP_STAGE: run the single-launch kernel on an already staged workspace
                                    (its rotation warps idle) instead of the two-launch attention kernel */
 

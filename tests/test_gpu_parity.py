@@ -23,7 +23,7 @@ BF16_TOL = 1e-2
 FP32_TOL = 1e-3
 # GTA_FLAG_* pipeline selectors of the product library: default single-launch pipeline (K/V rotation inside the attention
 # kernel), the two-launch pipeline (staging kernel + persistent attention kernel), V1 (non-persistent two-tile)
-PIPELINES, PIPELINE_IDS = [0, 32, 16], ["v3_fused", "v2_two_launch", "v1"]
+PIPELINES, PIPELINE_IDS = [0, 32, 256, 16], ["v3_fused", "v2_two_launch", "v4_streaming", "v1"]
 
 
 def _ops():
