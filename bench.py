@@ -1,11 +1,14 @@
 """Benchmark of the GTA-attention hot path (BASELINE.json metric: GTA-attention Mtokens/s at the MSN-Hard
 gta_so3 token shape; one process per GPU, batch-sharded, no collective in the forward).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload msn_enc|msn_dec|clevr_enc|clevr_dec|cfg1]
-    python bench.py --impl reference ...     # the reference's CPU path (torch restatement) on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload msn_enc|msn_dec|clevr_enc|clevr_dec|cfg1|sweep*]
+    python bench.py --impl reference ...     # the reference's own CPU path (baseline/_ref, else its torch restatement)
+    python bench.py --workload train_step_msn|train_step_clevr [--gpus N]    # BASELINE config 5: SRT train step, DDP
 
 A step = one pass of the hot path over one batch of synthetic input: rep construction (once per batch, as the
-reference does per encoder forward) + K'/V' staging + the fused attention kernel.  Prints ONE JSON line.
+reference does per encoder forward) + the fused GTA attention (ONE launch: K/V rotation by the staging warps of the
+attention kernel; `--flags 32` = the two-launch pipeline, `--flags 256` = two launches with the streaming-softmax
+kernel).  Prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -50,17 +53,18 @@ def peaks():
     return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def traffic_bytes(workload, batch):
-    """DRAM bytes (read + write) of one launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r01_traffic.json); null when no capture exists for this workload/batch."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def traffic_bytes(workload, batch, flags):
+    """DRAM bytes (read + write) of one launch of the dominant kernel, from the committed `ncu --set full` capture of this
+    very command (profiles/r02_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum; a profiler pass cannot run inside
+    the timed region).  Returns (bytes, provenance) or (None, None) when no capture exists for this workload/batch/flags."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
-        t = json.load(open(p))
-        if t["workload"] == workload and t["batch_per_gpu"] == batch:
-            return t["dram_bytes_read"] + t["dram_bytes_write"]
+        for t in json.load(open(p)):
+            if t["workload"] == workload and t["batch_per_gpu"] == batch and t.get("flags", 0) == flags:
+                return t["dram_bytes_read"] + t["dram_bytes_write"], "profiles/r02_traffic.json <- " + t["source"]
     except Exception:
         pass
-    return None
+    return None, None
 
 
 class ClockSampler(threading.Thread):
@@ -71,6 +75,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag, self.max_mhz = index, [], False, None
+        self.t_begin, self.t_end = 0.0, float("inf")      # only samples taken inside [t_begin, t_end] are reported
         self.nvml = None
         try:
             import pynvml
@@ -97,19 +102,25 @@ class ClockSampler(threading.Thread):
                 if self.nvml is not None:
                     mhz = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
                     mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
-                    self.samples.append((mhz, mask))
-                    time.sleep(0.002)
+                    self.samples.append((mhz, mask, time.perf_counter()))
+                    time.sleep(0.001)
                 else:
                     o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=clocks.sm,clocks.max.sm",
                                         "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                     f = [x.strip() for x in o.strip().split(",")]
-                    self.samples.append((float(f[0]), 0))
+                    self.samples.append((float(f[0]), 0, time.perf_counter()))
                     self.max_mhz = float(f[1])
             except Exception:
                 time.sleep(0.01)
 
+    def begin(self):
+        """The thread is started before the warm-up so that it is already polling; call this when the timed region starts."""
+        self.t_begin = time.perf_counter()
+
     def summary(self):
+        self.t_end = time.perf_counter()
         self.stop_flag = True
+        self.samples = [x for x in self.samples if self.t_begin <= x[2] <= self.t_end]
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
         sm = sorted(s[0] for s in self.samples)
@@ -121,8 +132,22 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def cpu_impl():
+    """(kind, description): "reference" when the unmodified reference is importable (baseline/_ref on the GPU box,
+    /root/reference in the build container), else "port" (oracle/torch_port.py, its ATen restatement)."""
+    from baseline import ref_loader
+    if ref_loader.available():
+        return "reference", ("the UNMODIFIED reference from %s: its own pre_compute_reps (source/encoder.py:183, "
+                             "source/decoder.py:247) + multihead_geometric_transform_attention (source/utils/gta.py:92) "
+                             "+ AttnFn (source/layers.py:202-211)" % ref_loader.root())
+    return "port", "oracle/torch_port.py (ATen restatement of the reference path; baseline/_ref is not installed)"
+
+
 def cpu_port_step(cfg, inp, tc=0.01):
-    """The reference's CPU path restated with the same ATen ops (oracle/torch_port.py), fp32."""
+    """One pass of the reference's CPU path, fp32: the reference itself when available, else its restatement."""
+    if cpu_impl()[0] == "reference":
+        from oracle import ref_harness as rh
+        return rh.ref_gta_attention(cfg, inp, trans_coeff=tc)[0]
     from oracle import torch_port as tp
     return tp.gta_attention(cfg, inp["q"], inp["k"], inp["v"], inp["extr_q"], inp["extr_k"], inp["coord_q"],
                             inp["coord_k"], trans_coeff=tc)
@@ -161,9 +186,10 @@ def cpu_baseline(cfg, args_w, budget_s=12.0, batch=2):
             best = min(best, time.perf_counter() - t1)
             reps += 1
     tokens = batch * nq * tq
-    return {"value": tokens / best / 1e6, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
-            "sample": f"oracle/torch_port.py (ATen restatement of the reference path), fp32, batch {batch} of the same "
-                      f"token shape, best of {reps}, {best*1e3:.1f} ms, thread count chosen as the fastest of a sweep"}
+    kind, desc = cpu_impl()
+    return {"value": tokens / best / 1e6, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": kind,
+            "sample": f"{desc}, fp32, batch {batch} of the same token shape, best of {reps}, {best*1e3:.1f} ms, "
+                      f"thread count chosen as the fastest of a sweep"}
 
 
 def run_reference(args, wl):
@@ -184,17 +210,183 @@ def run_reference(args, wl):
             cpu_port_step(cfg, inp)
         dt = (time.perf_counter() - t0) / args.steps
     val = batch * nq * tq / dt / 1e6
-    sample = (f"oracle/torch_port.py: the reference's CPU path restated with the same ATen ops (the reference is "
-              f"pure Python and is not present on the GPU box), fp32, {threads} threads (fastest of a sweep; host has "
-              f"{os.cpu_count()} cpus), batch {batch} per step")
+    kind, desc = cpu_impl()
+    sample = (f"{desc}, fp32, {threads} threads (fastest of a sweep; host has {os.cpu_count()} cpus), batch {batch} "
+              f"per step")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.workload, wl, batch),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def informational_legs(cfg, wl, B, dev_bufs, dev_small, views, cross, timed, steps):
+    """SURVEY 8(d) informational comparisons on the SAME device-resident inputs, outside `value`: the reference's own eager
+    function on the B200 (needs baseline/_ref) and the practical library bar — the reference's PyTorch rep rotation around
+    torch.nn.functional.scaled_dot_product_attention.  bf16 q/k/v, reps built by the reference's own pre_compute_reps
+    (fp32) once, outside the timed region (as the reference does per forward, not per layer)."""
+    from baseline import ref_loader
+    if not ref_loader.available():
+        return {"unavailable": "baseline/_ref is not installed (python baseline/install_ref.py)"}
+    base, nq, nk, tq, tk, _, _, _ = wl
+    try:
+        ref = ref_loader.load()
+        import torch.nn.functional as F
+        ek, ck = dev_small["extr_k"], dev_small["coord_k"]
+        extras = {"input_transforms": ek, "input_coord": ck.reshape(B, nk, -1, 2)}
+        akw = dict(f_dims=dict(cfg.f_dims), so2=cfg.so2, so3=cfg.so3, max_freq_h=cfg.max_freq_h, max_freq_w=cfg.max_freq_w,
+                   shared_freqs=cfg.shared_freqs)
+        enc = ref.encoder.ImprovedSRTEncoder.__new__(ref.encoder.ImprovedSRTEncoder)
+        orig_enc = gta_orig("enc") or ref.encoder.ImprovedSRTEncoder.pre_compute_reps
+        orig_enc(enc, akw, extras)
+        if cross:
+            extras["target_transforms"] = dev_small["extr_q"]
+            extras["target_coord"] = dev_small["coord_q"].reshape(B, nq, -1, 2)
+            dec = ref.decoder.ImprovedSRTDecoder.__new__(ref.decoder.ImprovedSRTDecoder)
+            (gta_orig("dec") or ref.decoder.ImprovedSRTDecoder.pre_compute_reps)(dec, akw, extras)
+        scale = cfg.head_dim ** -0.5
+
+        class Eager:            # AttnFn.forward, source/layers.py:207-211
+            def __call__(self, q, k, v):
+                attn = torch.softmax((q @ k.transpose(-1, -2)) * scale, -1)
+                return attn @ v, attn
+
+        class Sdpa:
+            def __call__(self, q, k, v):
+                return F.scaled_dot_product_attention(q, k, v, scale=scale), None
+        q, k, v = views(dev_bufs)
+        tc = torch.tensor([0.01], device=q.device)
+        fn = gta_orig("attn") or ref.gta.multihead_geometric_transform_attention
+        out = {}
+        for name, attn_fn in (("reference_eager_gpu", Eager()), ("reference_rotation_plus_sdpa_gpu", Sdpa())):
+            def run():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    fn(q, k, v, attn_fn=attn_fn, f_dims=dict(cfg.f_dims), reps=extras, trans_coeff=tc, v_transform=True,
+                       euclid=False)
+            try:
+                for _ in range(2):
+                    run()
+                ms = timed(run, max(3, steps // 5))
+                out[name] = {"ms": ms, "Mtokens_per_s": B * nq * tq / (ms * 1e-3) / 1e6}
+            except torch.cuda.OutOfMemoryError:
+                out[name] = {"unavailable": "out of memory (the eager path materialises [B,H,Tq,Tk])"}
+                torch.cuda.empty_cache()
+        out["note"] = ("same device-resident bf16 q/k/v and batch as `value`; reference from %s; reps prebuilt (not timed); "
+                       "CUDA events; informational only" % ref_loader.root())
+        return out
+    except Exception as e:      # never let an informational leg break the bench line
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
+def gta_orig(which):
+    """The reference's original callables when gta_b200.gta.install() has rebound them (it has not in this process unless
+    a train_step workload ran)."""
+    from gta_b200 import gta as fast
+    if which == "attn":
+        return fast._original
+    return fast._original_reps.get(which)
+
+
+def run_train_step(args):
+    """BASELINE config 5: one training step of the reference's TransformingSRT (built from its own YAML:
+    runs/msn/GTA/gta_so3 or runs/clevrtr/GTA/gta) on synthetic batches, global batch 32, AdamW, the config's precision
+    (MSN: bf16 autocast), encoder and decoder wrapped in DistributedDataParallel separately (train.py:182-188; the
+    collective is DDP's bucketed NCCL gradient all-reduce).  Timed twice on the same weights and batches: with the
+    drop-in installed (gta_b200.gta.install()) and with the reference's eager path.  value = samples/s of the installed
+    path over all ranks."""
+    from baseline import ref_loader, srt_synth
+    run = "msn/GTA/gta_so3" if args.workload == "train_step_msn" else "clevrtr/GTA/gta"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not ref_loader.available():
+        if rank == 0:
+            print(json.dumps({"metric": "SRT train step", "unavailable": "baseline/_ref is not installed"}), flush=True)
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    ref = ref_loader.load()
+    from gta_b200 import gta as fast
+    torch.manual_seed(0)
+    model, cfg = srt_synth.build_model(ref, run, dev)          # dropout as configured (0.01)
+    mixed = bool(cfg["training"].get("mixed_prec", False))
+    gb = 32
+    B = args.train_batch or max(1, gb // world)
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        model.encoder = DDP(model.encoder, device_ids=[local], output_device=local)
+        model.decoder = DDP(model.decoder, device_ids=[local], output_device=local)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    batches = [srt_synth.make_batch(run, B, dev, seed=100 * rank + i) for i in range(2)]
+    nparams = sum(p.numel() for p in model.parameters())
+
+    def train_step(i):
+        model.train()
+        opt.zero_grad(set_to_none=True)
+        loss, _ = srt_synth.loss_fn(model, batches[i % len(batches)], mixed)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed_steps(n):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            loss = train_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, float(loss.detach())
+
+    res = {}
+    steps = max(3, min(args.steps, 20))
+    for name in ("eager", "installed"):
+        if name == "installed":
+            fast.install()
+        else:
+            fast.uninstall()
+        for i in range(max(2, min(args.warmup, 3))):
+            train_step(i)
+        sampler = ClockSampler(local)
+        sampler.start()
+        sampler.begin()
+        res[name] = timed_steps(steps)
+        res[name + "_clocks"] = sampler.summary()
+    fast.uninstall()
+    if rank == 0:
+        ms_i, ms_e = res["installed"][0], res["eager"][0]
+        line = {"metric": "SRT encoder+decoder train step (samples/sec)", "value": world * B / (ms_i * 1e-3), "unit": "samples/s",
+                "n_gpus": world, "steps": steps, "warmup": 3, "ms_per_step": ms_i, "higher_is_better": True,
+                "scaling": "strong" if not args.train_batch else "weak", "vs_baseline": None,
+                "dtype": "bf16 autocast" if mixed else "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "run": "runs/%s/config.yaml" % run, "global_batch": world * B,
+                           "batch_per_gpu": B, "params": nparams, "optimizer": "AdamW",
+                           "parallelism": "DDP on encoder and decoder separately (train.py:182-188); NCCL bucketed gradient "
+                                          "all-reduce of %.0f MB fp32 per step" % (nparams * 4 / 1e6),
+                           "gta_layers": "5 encoder self-attention + 2 decoder cross-attention, forward and backward through "
+                                         "gta_attn_fwd / gta_attn_bwd, reps by gta_build_reps"},
+                "reference_eager": {"ms_per_step": ms_e, "samples_per_s": world * B / (ms_e * 1e-3), "clocks": res["eager_clocks"]},
+                "speedup_vs_reference_eager": ms_e / ms_i, "loss": {"installed": res["installed"][1], "eager": res["eager"][1]},
+                "clocks": res["installed_clocks"]}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def workload_config(name, wl, batch):
@@ -211,15 +403,20 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="msn_enc", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="msn_enc", choices=sorted(WORKLOADS) + ["train_step_msn", "train_step_clevr"])
+    ap.add_argument("--train-batch", type=int, default=0, help="train_step workloads: per-GPU batch (default: 32 / world, BASELINE config 5)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--flags", type=int, default=0, help="GTA_FLAG_* bits for gta_attn_fwd (1 = P in TMEM)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="batch chunks of the host-buffer pipeline (e2e leg)")
-    ap.add_argument("--backward", action="store_true", help="also time the fused backward (adds a `backward` object)")
+    ap.add_argument("--no-backward", action="store_true", help="skip the fused-backward leg (`backward` object)")
+    ap.add_argument("--backward", action="store_true", help="(kept for compatibility; the backward leg is on by default)")
+    ap.add_argument("--no-info", action="store_true", help="skip the informational GPU legs (reference eager / SDPA on the B200)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload.startswith("train_step"):
+        return run_train_step(args)
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, wl)
@@ -240,7 +437,7 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
 
-    from gta_b200 import _lib, ops
+    from gta_b200 import _lib, ops, shard
     _lib.lib()
 
     # ---- synthetic inputs, pinned on the host (e2e leg) and resident on the device (value leg)
@@ -300,9 +497,9 @@ def main():
     h2d()
     torch.cuda.synchronize()
     in_bytes = sum(t.numel() * t.element_size() for t in dev_bufs.values())
-    launches_per_step = (1 if not cfg.dims()[1] and not cfg.so3 else 1) + (1 if cross else 1) + (1 if cross else 0) + 2
-    # build_view_reps (1) + so2 tables (1 self / 2 cross) + staging (1) + attention (1)
-    launches_per_step = 1 + (2 if cross else 1) + 2
+    two_launch = bool(args.flags & (_lib.GTA_FLAG_TWO_LAUNCH | _lib.GTA_FLAG_V4_PIPELINE | _lib.GTA_FLAG_V1_PIPELINE))
+    # kernels per step: build_view_reps (1) + so2 tables (1 self / 2 cross) + [staging (1)] + attention (1)
+    launches_per_step = 1 + (2 if cross else 1) + (2 if two_launch else 1)
 
     def barrier():
         if dist is not None:
@@ -317,29 +514,31 @@ def main():
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = shard.max_over_ranks(e0.elapsed_time(e1), device=dev)     # whole-job time = the slowest rank
         barrier()
         return ms / n
 
+    sampler = ClockSampler(local)
+    sampler.start()                       # polling starts before the warm-up; only samples of the timed region are kept
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local)
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.begin()
     ms_step = timed(step, args.steps)
     clocks = sampler.summary()
 
-    # ---- dominant kernel alone (K'/V' already staged in the workspace): roofline numerator
+    # ---- the library call alone (reps already built): the dominant launch, roofline numerator
     _, reps = step()
     q, k, v = views(dev_bufs)
+    op_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, flags=args.flags)
     attn_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc,
-                                              flags=args.flags | _lib.GTA_FLAG_SKIP_STAGE)
+                                              flags=(args.flags & ~_lib.GTA_FLAG_TWO_LAUNCH) | _lib.GTA_FLAG_TWO_LAUNCH | _lib.GTA_FLAG_SKIP_STAGE)
     stage_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc,
                                                flags=args.flags | _lib.GTA_FLAG_STAGE_ONLY)
+    for _ in range(3):
+        op_only()
+    ms_op = timed(op_only, args.steps)
+    stage_only()                                  # (re)stage the workspace for the attention-only measurement
     for _ in range(3):
         attn_only()
     ms_attn = timed(attn_only, args.steps)
@@ -364,37 +563,57 @@ def main():
                "api": "gta_b200.host.HostStagedAttention.run: %d batch chunks, H2D / compute / D2H on three streams" % len(pipe.bounds)}
 
     bwd = None
-    if args.backward:
+    if not args.no_backward:
         out_f, lse_f = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True)
         dout = torch.randn(out_f.shape, device=dev).to(out_f.dtype)
         bwd_fn = lambda: ops.gta_attention_bwd(dout, q, k, v, out_f, lse_f, reps, cfg.f_dims, trans_coeff=tc)
         for _ in range(3):
             bwd_fn()
-        ms_bwd = timed(bwd_fn, args.steps)
+        ms_bwd = timed(bwd_fn, max(3, args.steps // 2))
+        bwd_flops = 2.5 * 4.0 * B * H * nq * tq * nk * tk * D
+        pk_b, _ = peaks()
         bwd = {"ms": ms_bwd, "kernels": "K'/V'/Q'/dO' staging + delta + attn_bwd_kernel<dKV> + attn_bwd_kernel<dQ>",
-               "tflops_algorithmic": 2.5 * 4.0 * B * H * nq * tq * nk * tk * D / (ms_bwd * 1e-3) / 1e12,
+               "tflops_algorithmic": bwd_flops / (ms_bwd * 1e-3) / 1e12,
+               "frac_of_peak": bwd_flops / (ms_bwd * 1e-3) / 1e12 / pk_b["bf16_tflops"],
                "fwd_bwd_Mtokens_per_s": world * B * nq * tq / ((ms_step + ms_bwd) * 1e-3) / 1e6}
+        del out_f, lse_f, dout
+
+    info = None
+    if not args.no_info and rank == 0:
+        info = informational_legs(cfg, wl, B, dev_bufs, dev_small, views, cross, timed, args.steps)
 
     if rank == 0:
         Tq, Tk = nq * tq, nk * tk
         flops = 4.0 * B * H * Tq * Tk * D
         pk, pk_src = peaks()
         total_s = ms_step * 1e-3 * args.steps
-        peak = pk["bf16_tflops"] if total_s < 2.0 else pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-        achieved = flops / (ms_attn * 1e-3) / 1e12
+        burst = total_s < 2.0
+        peak = pk["bf16_tflops"] if burst else pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        ms_dom = ms_attn if two_launch else ms_op
+        achieved = flops / (ms_dom * 1e-3) / 1e12
+        if args.flags & _lib.GTA_FLAG_V4_PIPELINE:
+            kname = "attn_fwd5_kernel (streaming softmax + epilogue warpgroup; K'/V' staged by rotate_kv_kernel)"
+        elif two_launch:
+            kname = "attn_fwd3_kernel (persistent two-tile pipeline; K'/V' staged by rotate_kv_kernel)"
+        else:
+            kname = "attn_fwd4_kernel (ONE launch: K/V rotation by staging warps + persistent two-tile attention pipeline)"
+        traffic, traffic_src = traffic_bytes(args.workload, B, args.flags)
         line = {
-            "metric": METRIC, "value": world * B * Tq / (ms_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": shard.job_throughput(B * Tq, world, ms_step) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(args.workload, wl, B),
                            l2="q/k/v inputs %.0f MB per step > 126 MB L2 (no explicit flush needed)" % (in_bytes / 1e6)
                            if in_bytes > 126e6 else "inputs %.0f MB fit L2; not flushed" % (in_bytes / 1e6),
-                           p_operand="tmem" if args.flags & 1 else "smem"),
+                           p_operand="tmem (TS form of tcgen05.mma: P read from tensor memory)",
+                           pipeline="single launch" if not two_launch else "two launches", flags=args.flags),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": traffic_bytes(args.workload, B),
-                         "kernel": "attn_fwd3_kernel (persistent two-tile pipeline)", "kernel_ms": ms_attn, "stage_kernel_ms": ms_stage,
-                         "flops_per_launch": flops, "peak_source": pk_src +
-                         (" burst" if total_s < 2.0 else " sustained")},
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": kname, "kernel_ms": ms_dom,
+                         "step_frac": flops / (ms_step * 1e-3) / 1e12 / peak,
+                         "step_note": "step_frac = the same FLOPs over the whole step (rep construction + every launch)",
+                         "two_launch_attention_kernel_ms": ms_attn, "staging_kernel_ms": ms_stage, "library_call_ms": ms_op,
+                         "flops_per_launch": flops, "peak_source": pk_src + (" burst" if burst else " sustained")},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
@@ -402,6 +621,8 @@ def main():
             line["e2e"] = e2e
         if bwd:
             line["backward"] = bwd
+        if info:
+            line["informational"] = info
         if not args.no_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline(cfg, wl)
         print(json.dumps(line), flush=True)

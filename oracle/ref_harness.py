@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE — not product code.  Drives the *unmodified* reference (autonomousvision/gta,
-mounted read-only at /root/reference) to validate the oracle restatements and to generate the
-golden vectors under tests/golden/.  Only usable in the build container: /root/reference does not
-exist on the GPU box, so nothing under `-m gpu`, smoke() or bench.py imports this module.
+mounted read-only at /root/reference in the build container; its model files installed unmodified into
+baseline/_ref for the GPU box, see baseline/install_ref.py) to validate the oracle restatements, to generate
+the golden vectors under tests/golden/, and to time the reference's own CPU path (bench.py --impl reference
+and the cpu_baseline leg).  Never imported by the product package.
 
 What it calls in the reference (no reference source is copied here):
   * ImprovedSRTEncoder.pre_compute_reps   source/encoder.py:183-265   (self-attention reps)
@@ -22,47 +23,19 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("GTA_REF", "/root/reference")
-_mods = None
+_HERE = os.path.dirname(os.path.abspath(__file__))
+if os.path.dirname(_HERE) not in sys.path:
+    sys.path.insert(0, os.path.dirname(_HERE))
+from baseline import ref_loader  # noqa: E402  ($GTA_REF, /root/reference or baseline/_ref; handles the import quirks)
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_ROOT, "source", "utils", "gta.py"))
-
-
-@contextlib.contextmanager
-def _cwd(path):
-    old = os.getcwd()
-    os.chdir(path)
-    try:
-        yield
-    finally:
-        os.chdir(old)
+    return ref_loader.available()
 
 
 def load():
-    """Import the reference modules once; returns a namespace with gta, wigner_d, encoder, decoder."""
-    global _mods
-    if _mods is not None:
-        return _mods
-    if not available():
-        raise RuntimeError("reference tree not found at %s" % REF_ROOT)
-    sys.dont_write_bytecode = True
-    with _cwd(REF_ROOT):
-        sys.path.insert(0, REF_ROOT)
-        try:
-            import source.utils.gta as rgta
-            if not hasattr(rgta, "ray2rotation"):
-                def _stub(*a, **k):
-                    raise NotImplementedError("ray2rotation is undefined in the reference")
-                rgta.ray2rotation = _stub
-            import source.utils.wigner_d as rwig
-            import source.encoder as renc
-            import source.decoder as rdec
-        finally:
-            sys.path.remove(REF_ROOT)
-    _mods = types.SimpleNamespace(gta=rgta, wigner_d=rwig, encoder=renc, decoder=rdec)
-    return _mods
+    """The reference modules: namespace(gta, wigner_d, layers, encoder, decoder, models_nvs, root)."""
+    return ref_loader.load()
 
 
 class _AttnFn:
