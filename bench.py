@@ -6,9 +6,9 @@ gta_so3 token shape; one process per GPU, batch-sharded, no collective in the fo
     python bench.py --workload train_step_msn|train_step_clevr [--gpus N]    # BASELINE config 5: SRT train step, DDP
 
 A step = one pass of the hot path over one batch of synthetic input: rep construction (once per batch, as the
-reference does per encoder forward) + the fused GTA attention (ONE launch: K/V rotation by the staging warps of the
-attention kernel; `--flags 32` = the two-launch pipeline, `--flags 256` = two launches with the streaming-softmax
-kernel).  Prints ONE JSON line.
+reference does per encoder forward) + K'/V' staging + the fused attention kernel (`--flags 32` = ONE launch: K/V
+rotation by staging warps of the attention kernel; `--flags 256` / `512` = the streaming-softmax / spare-P-buffer
+attention kernels).  Prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -497,7 +497,7 @@ def main():
     h2d()
     torch.cuda.synchronize()
     in_bytes = sum(t.numel() * t.element_size() for t in dev_bufs.values())
-    two_launch = bool(args.flags & (_lib.GTA_FLAG_TWO_LAUNCH | _lib.GTA_FLAG_V4_PIPELINE | _lib.GTA_FLAG_V1_PIPELINE))
+    two_launch = not (args.flags & _lib.GTA_FLAG_SINGLE_LAUNCH)
     # kernels per step: build_view_reps (1) + so2 tables (1 self / 2 cross) + [staging (1)] + attention (1)
     launches_per_step = 1 + (2 if cross else 1) + (2 if two_launch else 1)
 
@@ -532,7 +532,7 @@ def main():
     q, k, v = views(dev_bufs)
     op_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, flags=args.flags)
     attn_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc,
-                                              flags=(args.flags & ~_lib.GTA_FLAG_TWO_LAUNCH) | _lib.GTA_FLAG_TWO_LAUNCH | _lib.GTA_FLAG_SKIP_STAGE)
+                                              flags=(args.flags & ~_lib.GTA_FLAG_SINGLE_LAUNCH) | _lib.GTA_FLAG_SKIP_STAGE)
     stage_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc,
                                                flags=args.flags | _lib.GTA_FLAG_STAGE_ONLY)
     for _ in range(3):
@@ -591,7 +591,9 @@ def main():
         peak = pk["bf16_tflops"] if burst else pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
         ms_dom = ms_attn if two_launch else ms_op
         achieved = flops / (ms_dom * 1e-3) / 1e12
-        if args.flags & _lib.GTA_FLAG_V4_PIPELINE:
+        if args.flags & _lib.GTA_FLAG_V5_PIPELINE:
+            kname = "attn_fwd6_kernel (persistent two-tile pipeline with the spare P buffer; K'/V' staged by rotate_kv_kernel)"
+        elif args.flags & _lib.GTA_FLAG_V4_PIPELINE:
             kname = "attn_fwd5_kernel (streaming softmax + epilogue warpgroup; K'/V' staged by rotate_kv_kernel)"
         elif two_launch:
             kname = "attn_fwd3_kernel (persistent two-tile pipeline; K'/V' staged by rotate_kv_kernel)"

@@ -20,9 +20,10 @@ GTA_FLAG_STAGE_ONLY = 4
 GTA_FLAG_V0_PIPELINE = 8
 GTA_FLAG_FAST_FP32 = 128
 GTA_FLAG_V1_PIPELINE = 16
-GTA_FLAG_TWO_LAUNCH = 32
+GTA_FLAG_SINGLE_LAUNCH = 32
 GTA_FLAG_V3_PRESTAGED = 64
 GTA_FLAG_V4_PIPELINE = 256
+GTA_FLAG_V5_PIPELINE = 512
 
 
 class GtaReps(ctypes.Structure):

@@ -43,6 +43,7 @@ int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v2(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v3(const GtaAttnParams& p, bool fused, cudaStream_t st);
 int launch_attn_fwd_v4(const GtaAttnParams& p, cudaStream_t st, bool* handled);
+int launch_attn_fwd_v5(const GtaAttnParams& p, cudaStream_t st);
 int launch_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
                          cudaStream_t st);
 int launch_umma_bench(int D, int mode, int reps, int grid, long long* out, cudaStream_t st);
@@ -64,8 +65,9 @@ inline size_t kv_flags_offset(int B, int H, int Tk, int D) { return 2 * static_c
 inline size_t kv_flags_bytes(int B, int H, int Tk) { return (static_cast<size_t>(B) * H * num_kv_tiles(Tk) * sizeof(int) + 1023) / 1024 * 1024; }
 // Which parameter sets the fused single-launch kernel (gta_attn_fwd4.cu) serves.
 inline bool attn_is_fused_launch(const GtaAttnParams& p) {
-    return !attn_is_split_precision(p) && p.D <= 96 &&
-           !(p.flags & (GTA_FLAG_SKIP_STAGE | GTA_FLAG_STAGE_ONLY | GTA_FLAG_V0_PIPELINE | GTA_FLAG_V1_PIPELINE | GTA_FLAG_TWO_LAUNCH | GTA_FLAG_V4_PIPELINE));
+    return (p.flags & GTA_FLAG_SINGLE_LAUNCH) && !attn_is_split_precision(p) && p.D <= 96 &&
+           !(p.flags & (GTA_FLAG_SKIP_STAGE | GTA_FLAG_STAGE_ONLY | GTA_FLAG_V0_PIPELINE | GTA_FLAG_V1_PIPELINE | GTA_FLAG_V4_PIPELINE |
+                        GTA_FLAG_V5_PIPELINE));
 }
 
 }  // namespace gta

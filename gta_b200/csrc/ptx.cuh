@@ -3,6 +3,7 @@
 // DESIGN.md §"tcgen05 descriptors").
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_bf16.h>
 
 namespace gta {
@@ -48,10 +49,26 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Debug builds (-DGTA_MBAR_TIMEOUT=<clocks>) turn an endless wait into a report + trap: which barrier (byte offset in
+// shared memory), which parity, which thread.  Production builds spin (try_wait suspends the thread in hardware).
+#ifdef GTA_MBAR_TIMEOUT
+static __device__ __noinline__ void mbar_timeout_report(uint32_t bar_saddr, uint32_t parity) {
+    printf("gta_b200: mbarrier wait timed out: block %d thread %d barrier@smem+%u parity %u\n", blockIdx.x, threadIdx.x,
+           bar_saddr, parity);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > static_cast<long long>(GTA_MBAR_TIMEOUT)) mbar_timeout_report(smem_u32(bar), parity);
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+#endif
 
 // Make generic-proxy shared-memory writes visible to the async proxy (UMMA operand reads, bulk copies).
 __device__ __forceinline__ void fence_proxy_async_smem() {

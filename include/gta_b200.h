@@ -102,11 +102,14 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_FAST_FP32 128 /* fp32 inputs: multiply in plain bf16 (1e-2 budget) instead of the split-precision path */
 #define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 #define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
-#define GTA_FLAG_TWO_LAUNCH 32  /* previous default, kept for A/B measurement: K'/V' staging kernel + persistent attention kernel
-                                   (two launches).  Without it bf16 / fast-fp32 calls with D <= 96 run ONE launch: the K/V
-                                   rotation is done by staging warps of the attention kernel itself (gta_attn_fwd4.cu) */
+#define GTA_FLAG_SINGLE_LAUNCH 32 /* ONE launch for K/V rotation + attention (gta_attn_fwd4.cu): the rotation is done by staging warps of
+                                   the persistent attention kernel itself, K'/V' tile images go through L2 with per-tile ready
+                                   flags.  bf16 / fast-fp32 inputs, D <= 96.  Measured 2-3 % slower than the default two-launch
+                                   pipeline (staging kernel + attention kernel) at 0.89x its DRAM traffic, see DESIGN.md */
 #define GTA_FLAG_V4_PIPELINE 256 /* two launches with the streaming-softmax / epilogue-warpgroup attention kernel (gta_attn_fwd5.cuh);
                                     head layouts without an instantiation fall back to the gta_attn_fwd3.cu kernel */
+#define GTA_FLAG_V5_PIPELINE 512 /* two launches; attention kernel with the spare P buffer in tensor memory (gta_attn_fwd6.cu): QK_X(j+1) is
+                                    issued while the exponentials of tile j still run, on every other key tile */
 #define GTA_FLAG_V3_PRESTAGED 64 /* with GTA_FLAG_SKIP_STAGE: run the single-launch kernel on an already staged workspace
                                    (its rotation warps idle) instead of the two-launch attention kernel */
 

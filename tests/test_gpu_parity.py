@@ -21,9 +21,10 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 BF16_TOL = 1e-2
 FP32_TOL = 1e-3
-# GTA_FLAG_* pipeline selectors of the product library: default single-launch pipeline (K/V rotation inside the attention
-# kernel), the two-launch pipeline (staging kernel + persistent attention kernel), V1 (non-persistent two-tile)
-PIPELINES, PIPELINE_IDS = [0, 32, 256, 16], ["v3_fused", "v2_two_launch", "v4_streaming", "v1"]
+# GTA_FLAG_* pipeline selectors of the product library: the default two-launch pipeline (staging kernel + persistent
+# attention kernel), the single-launch pipeline (K/V rotation by staging warps of the attention kernel), the
+# streaming-softmax / epilogue-warpgroup kernel, the spare-P-buffer kernel, V1 (non-persistent two-tile)
+PIPELINES, PIPELINE_IDS = [0, 32, 256, 512, 16], ["v2_two_launch", "v3_single_launch", "v4_streaming", "v5_spare_p", "v1"]
 
 
 def _ops():

@@ -9,7 +9,7 @@ for lib in ${LIBS:-libgta_b200.so}; do
     python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/bench_q.json")); r=d["roofline"]; print("$lib flags=$fl", round(d["value"],1), "Mtok/s step_ms", round(d["ms_per_step"],4), "attn_ms", round(r["kernel_ms"],4), "stage_ms", round(r["stage_kernel_ms"],3), d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+    d=json.load(open("gpurun_out/bench_q.json")); r=d["roofline"]; print("$lib flags=$fl", round(d["value"],1), "Mtok/s step_ms", round(d["ms_per_step"],4), "dom_kernel_ms", round(r["kernel_ms"],4), "attn2L_ms", round(r["two_launch_attention_kernel_ms"],4), "stage_ms", round(r["staging_kernel_ms"],3), d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 except Exception as e: print("failed", e); print(open("gpurun_out/bench_q.err").read()[-1500:])
 PY
   done

@@ -10,7 +10,7 @@ bench_one() {  # name, lib, extra args
   python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/bench_$name.json")); r=d["roofline"]; print("$name", round(d["value"],1), "Mtok/s step_ms", round(d["ms_per_step"],4), "attn_ms", round(r["kernel_ms"],4), "stage_ms", round(r["stage_kernel_ms"],3), d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+    d=json.load(open("gpurun_out/bench_$name.json")); r=d["roofline"]; print("$name", round(d["value"],1), "Mtok/s step_ms", round(d["ms_per_step"],4), "dom_kernel_ms", round(r["kernel_ms"],4), "attn2L_ms", round(r["two_launch_attention_kernel_ms"],4), "stage_ms", round(r["staging_kernel_ms"],3), d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 except Exception as e: print("$name failed", e); print(open("gpurun_out/bench_$name.err").read()[-1500:])
 PY
 }
