@@ -6,9 +6,10 @@ gta_so3 token shape; one process per GPU, batch-sharded, no collective in the fo
     python bench.py --workload train_step_msn|train_step_clevr [--gpus N]    # BASELINE config 5: SRT train step, DDP
 
 A step = one pass of the hot path over one batch of synthetic input: rep construction (once per batch, as the
-reference does per encoder forward) + K'/V' staging + the fused attention kernel (`--flags 32` = ONE launch: K/V
-rotation by staging warps of the attention kernel; `--flags 256` / `512` = the streaming-softmax / spare-P-buffer
-attention kernels).  Prints ONE JSON line.
+reference does per encoder forward) + the library call gta_attn_fwd, which picks its pipeline from the shape (one launch
+with the K/V rotation done by staging warps of the attention kernel, or staging kernel + attention kernel; `--flags 32`
+/ `1024` force one / two launches, `--flags 256` / `512` select the streaming-softmax / spare-P-buffer attention kernels).
+Prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -497,7 +498,9 @@ def main():
     h2d()
     torch.cuda.synchronize()
     in_bytes = sum(t.numel() * t.element_size() for t in dev_bufs.values())
-    two_launch = not (args.flags & _lib.GTA_FLAG_SINGLE_LAUNCH)
+    _q, _k, _v = views(dev_bufs)
+    pipeline = ops.pipeline_of(_q, _k, _v, ops.PackedReps(n_q_views=nq, n_k_views=nk), cfg.f_dims, flags=args.flags)
+    two_launch = pipeline != "single launch"
     # kernels per step: build_view_reps (1) + so2 tables (1 self / 2 cross) + [staging (1)] + attention (1)
     launches_per_step = 1 + (2 if cross else 1) + (2 if two_launch else 1)
 
@@ -532,9 +535,9 @@ def main():
     q, k, v = views(dev_bufs)
     op_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, flags=args.flags)
     attn_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc,
-                                              flags=(args.flags & ~_lib.GTA_FLAG_SINGLE_LAUNCH) | _lib.GTA_FLAG_SKIP_STAGE)
+                                              flags=(args.flags & ~_lib.GTA_FLAG_SINGLE_LAUNCH) | _lib.GTA_FLAG_TWO_LAUNCH | _lib.GTA_FLAG_SKIP_STAGE)
     stage_only = lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc,
-                                               flags=args.flags | _lib.GTA_FLAG_STAGE_ONLY)
+                                               flags=(args.flags & ~_lib.GTA_FLAG_SINGLE_LAUNCH) | _lib.GTA_FLAG_STAGE_ONLY)
     for _ in range(3):
         op_only()
     ms_op = timed(op_only, args.steps)
@@ -608,7 +611,7 @@ def main():
                            l2="q/k/v inputs %.0f MB per step > 126 MB L2 (no explicit flush needed)" % (in_bytes / 1e6)
                            if in_bytes > 126e6 else "inputs %.0f MB fit L2; not flushed" % (in_bytes / 1e6),
                            p_operand="tmem (TS form of tcgen05.mma: P read from tensor memory)",
-                           pipeline="single launch" if not two_launch else "two launches", flags=args.flags),
+                           pipeline=pipeline + (" (chosen by the library from the shape)" if not args.flags & (_lib.GTA_FLAG_SINGLE_LAUNCH | _lib.GTA_FLAG_TWO_LAUNCH) else " (forced by --flags)"), flags=args.flags),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": kname, "kernel_ms": ms_dom,

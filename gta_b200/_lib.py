@@ -14,13 +14,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GTA_B200_LIB") or os.path.join(_HERE, "libgta_b200.so")
 
 GTA_DTYPE_BF16, GTA_DTYPE_F32 = 0, 1
-GTA_FLAG_P_IN_TMEM = 1
 GTA_FLAG_SKIP_STAGE = 2
 GTA_FLAG_STAGE_ONLY = 4
-GTA_FLAG_V0_PIPELINE = 8
 GTA_FLAG_FAST_FP32 = 128
 GTA_FLAG_V1_PIPELINE = 16
 GTA_FLAG_SINGLE_LAUNCH = 32
+GTA_FLAG_TWO_LAUNCH = 1024
+GTA_PIPELINE_NAMES = {0: "two launches", 1: "single launch", 2: "split precision", 3: "generic"}
 GTA_FLAG_V3_PRESTAGED = 64
 GTA_FLAG_V4_PIPELINE = 256
 GTA_FLAG_V5_PIPELINE = 512
@@ -55,6 +55,7 @@ SYMBOLS = {
     "gta_attn_fwd_workspace_bytes_ex": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "gta_attn_fwd_workspace_bytes_p": (c_size_t, [POINTER(GtaAttnParams)]),
     "gta_attn_fwd": (c_int, [POINTER(GtaAttnParams), c_void_p]),
+    "gta_attn_fwd_pipeline": (c_int, [POINTER(GtaAttnParams)]),
     "gta_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "gta_attn_bwd": (c_int, [POINTER(GtaAttnBwdParams), c_void_p]),
     "gta_attn_probs_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
@@ -65,14 +66,22 @@ SYMBOLS = {
     "gta_wigner_d": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "gta_se3_inverse": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gta_t2_mats": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "gta_umma_probe": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 3),
-    "gta_umma_bench": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "gta_softmax_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gta_last_error": (c_char_p, []),
     "gta_abi_version": (c_int, []),
 }
 
+# development hooks (include/gta_b200_dev.h -> libgta_b200_dev.so): probes, micro-benchmarks, the first-generation kernel
+DEV_LIB_PATH = os.path.join(_HERE, "libgta_b200_dev.so")
+DEV_SYMBOLS = {
+    "gta_dev_umma_probe": (c_int, [c_void_p] * 4 + [c_int, c_int] + [c_void_p] * 3),
+    "gta_dev_umma_bench": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "gta_dev_softmax_bench": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gta_dev_attn_fwd_v0": (c_int, [POINTER(GtaAttnParams), c_void_p]),
+    "gta_dev_last_error": (c_char_p, []),
+}
+
 _lib = None
+_dev = None
 
 
 class GtaError(RuntimeError):
@@ -92,6 +101,25 @@ def lib() -> ctypes.CDLL:
             fn.restype, fn.argtypes = res, args
         _lib = l
     return _lib
+
+
+def dev_lib() -> ctypes.CDLL:
+    """The development library (tests / tools only)."""
+    global _dev
+    if _dev is None:
+        if not os.path.exists(DEV_LIB_PATH):
+            raise GtaError("gta_b200: %s is missing — build it with `python -m gta_b200.build`" % DEV_LIB_PATH)
+        l = ctypes.CDLL(DEV_LIB_PATH)
+        for name, (res, args) in DEV_SYMBOLS.items():
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = res, args
+        _dev = l
+    return _dev
+
+
+def check_dev(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise GtaError("%s failed (rc=%d): %s" % (what or "gta_b200 dev call", rc, dev_lib().gta_dev_last_error().decode()))
 
 
 def check(rc: int, what: str = "") -> None:

@@ -12,7 +12,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgta_b200.so")
-SOURCES = ["gta_abi.cu", "gta_reps.cu", "gta_rotate_kv.cu", "gta_generic.cu", "gta_attn_fwd.cu", "gta_attn_fwd2.cu", "gta_attn_fwd3.cu", "gta_attn_fwd4.cu", "gta_attn_fwd5a.cu", "gta_attn_fwd5b.cu", "gta_attn_fwd6.cu", "gta_attn_fwd_hp.cu", "gta_attn_bwd.cu"]
+SOURCES = ["gta_abi.cu", "gta_reps.cu", "gta_rotate_kv.cu", "gta_generic.cu", "gta_attn_fwd2.cu", "gta_attn_fwd3.cu", "gta_attn_fwd4.cu", "gta_attn_fwd5a.cu", "gta_attn_fwd5b.cu", "gta_attn_fwd6.cu", "gta_attn_fwd_hp.cu", "gta_attn_bwd.cu"]
+# development library (probes, micro-benchmarks, the first-generation kernel): include/gta_b200_dev.h
+DEV_SOURCES = ["gta_dev_abi.cu", "gta_attn_fwd.cu"]
+DEV_OUT = os.path.join(HERE, "libgta_b200_dev.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -24,7 +27,7 @@ def _nvcc() -> str:
 
 
 def _stale() -> bool:
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(DEV_OUT):
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "gta_b200.h")]
@@ -44,9 +47,11 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
         common += ["-Xptxas", "-v"]
     objs = []
     procs = []
-    for src in SOURCES:
+    dev_objs = [os.path.join(objdir, src.replace(".cu", ".o")) for src in DEV_SOURCES]
+    for src in SOURCES + DEV_SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        objs.append(obj)
+        if src in SOURCES:
+            objs.append(obj)
         procs.append((src, subprocess.Popen(common + ["-c", os.path.join(CSRC, src), "-o", obj],
                                             stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
@@ -56,6 +61,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
     subprocess.check_call([nvcc, *ARCH, "-shared", "-o", out, *objs, "-lcudart"])
+    if out == OUT:
+        subprocess.check_call([nvcc, *ARCH, "-shared", "-o", DEV_OUT, *dev_objs, "-lcudart"])
     return out
 
 

@@ -39,7 +39,7 @@ int launch_rotate_kv(const GtaAttnParams& p, cudaStream_t st);
 int launch_rotate_q_do(const GtaAttnParams& p, const void* dout, uint8_t* q_img, uint8_t* do_img, cudaStream_t st);
 int launch_rotate_debug(const GtaAttnParams& p, float* qt, float* kt, float* vt, cudaStream_t st);
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st);
-int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);
+int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st);   // dev library only (gta_dev_abi.cu)
 int launch_attn_fwd_v2(const GtaAttnParams& p, cudaStream_t st);
 int launch_attn_fwd_v3(const GtaAttnParams& p, bool fused, cudaStream_t st);
 int launch_attn_fwd_v4(const GtaAttnParams& p, cudaStream_t st, bool* handled);
@@ -65,9 +65,15 @@ inline size_t kv_flags_offset(int B, int H, int Tk, int D) { return 2 * static_c
 inline size_t kv_flags_bytes(int B, int H, int Tk) { return (static_cast<size_t>(B) * H * num_kv_tiles(Tk) * sizeof(int) + 1023) / 1024 * 1024; }
 // Which parameter sets the fused single-launch kernel (gta_attn_fwd4.cu) serves.
 inline bool attn_is_fused_launch(const GtaAttnParams& p) {
-    return (p.flags & GTA_FLAG_SINGLE_LAUNCH) && !attn_is_split_precision(p) && p.D <= 96 &&
-           !(p.flags & (GTA_FLAG_SKIP_STAGE | GTA_FLAG_STAGE_ONLY | GTA_FLAG_V0_PIPELINE | GTA_FLAG_V1_PIPELINE | GTA_FLAG_V4_PIPELINE |
-                        GTA_FLAG_V5_PIPELINE));
+    if (attn_is_split_precision(p) || p.D > 96) return false;
+    if (p.flags & (GTA_FLAG_SKIP_STAGE | GTA_FLAG_STAGE_ONLY | GTA_FLAG_V1_PIPELINE | GTA_FLAG_V4_PIPELINE | GTA_FLAG_V5_PIPELINE |
+                   GTA_FLAG_TWO_LAUNCH))
+        return false;
+    if (p.flags & GTA_FLAG_SINGLE_LAUNCH) return true;
+    // automatic choice (measured on B200): the staging warps of the single-launch kernel rotate 2*Tk/Tq key tiles
+    // per work item; large calls that need more than one per item run 2 % faster with the stand-alone staging kernel
+    const double flops = 4.0 * p.B * p.H * static_cast<double>(p.Tq) * p.Tk * p.D;
+    return !(2.0 * p.Tk > 1.0 * p.Tq && flops > 1e11);
 }
 
 }  // namespace gta

@@ -64,7 +64,7 @@ using namespace gta;
 extern "C" {
 
 const char* gta_last_error(void) { return g_err; }
-int gta_abi_version(void) { return 3; }
+int gta_abi_version(void) { return 4; }
 
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D) {
     if (B <= 0 || H <= 0 || Tk <= 0 || D <= 0) return 0;
@@ -81,6 +81,13 @@ size_t gta_attn_fwd_workspace_bytes_p(const GtaAttnParams* p) {
     if (!p || p->B <= 0 || p->H <= 0 || p->Tq <= 0 || p->Tk <= 0 || p->D <= 0) return 0;
     if (attn_needs_generic(*p)) return generic_workspace_bytes(*p);
     return gta_attn_fwd_workspace_bytes_ex(p->B, p->H, p->Tk, p->D, p->in_dtype, p->flags);
+}
+
+int gta_attn_fwd_pipeline(const GtaAttnParams* p) {
+    if (!p) return GTA_ERR_INVALID;
+    if (attn_needs_generic(*p)) return GTA_PIPELINE_GENERIC;
+    if (attn_is_split_precision(*p)) return GTA_PIPELINE_SPLIT_PRECISION;
+    return attn_is_fused_launch(*p) ? GTA_PIPELINE_SINGLE_LAUNCH : GTA_PIPELINE_TWO_LAUNCH;
 }
 
 int gta_attn_fwd(const GtaAttnParams* p, void* stream) {
@@ -152,20 +159,6 @@ int gta_t2_mats(const float* coord, int64_t n, float* mats, float* inv_mats, voi
 
 int gta_wigner_d(const float* R, int64_t n, float* d1, float* d2, void* stream) {
     return launch_wigner(R, n, d1, d2, static_cast<cudaStream_t>(stream));
-}
-
-int gta_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem, float* outS,
-                   float* outO, void* stream) {
-    return launch_umma_probe(A, Bm, P, V, D, p_in_tmem, outS, outO, static_cast<cudaStream_t>(stream));
-}
-
-int gta_umma_bench(int D, int mode, int reps, int grid, long long* out, void* stream) {
-    return launch_umma_bench(D, mode, reps, grid, out, static_cast<cudaStream_t>(stream));
-}
-
-int gta_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
-                      void* stream) {
-    return launch_softmax_bench(num, den, warps, reps, grid, in, out, clk, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -335,7 +335,7 @@ static int launch_t(const GtaAttnParams& p, const AttnArgs& a, dim3 grid, cudaSt
 int launch_attn_fwd_v0(const GtaAttnParams& p, cudaStream_t st) {
     const AttnArgs a = make_attn_args(p);
     dim3 grid((p.Tq + 127) / 128, p.H, p.B);
-    if (p.flags & GTA_FLAG_P_IN_TMEM) return launch_t<true>(p, a, grid, st);
+    if (p.flags & 1 /* P operand in tensor memory */) return launch_t<true>(p, a, grid, st);
     return launch_t<false>(p, a, grid, st);
 }
 

@@ -372,7 +372,6 @@ static int launch2_d(const AttnArgs& a, int D, dim3 grid, cudaStream_t st) {
 }
 
 int launch_attn_fwd(const GtaAttnParams& p, cudaStream_t st) {
-    if (p.flags & GTA_FLAG_V0_PIPELINE) return launch_attn_fwd_v0(p, st);
     if (!(p.flags & GTA_FLAG_V1_PIPELINE) && p.D <= 96) {
         if (p.flags & GTA_FLAG_V5_PIPELINE) return launch_attn_fwd_v5(p, st);
         if (p.flags & GTA_FLAG_V4_PIPELINE) {

@@ -283,8 +283,18 @@ def wigner_d(R: torch.Tensor):
 
 
 def umma_probe(A, Bm, P, V, p_in_tmem: bool):
+    """tcgen05 descriptor / tile-image self-test (development library)."""
     D = A.shape[1]
     outS = torch.empty(128, 128, device=A.device, dtype=torch.float32)
     outO = torch.empty(128, D, device=A.device, dtype=torch.float32)
-    _launch(A.device, "gta_umma_probe", _ptr(A), _ptr(Bm), _ptr(P), _ptr(V), D, int(p_in_tmem), _ptr(outS), _ptr(outO))
+    with torch.cuda.device(A.device):
+        _lib.check_dev(_lib.dev_lib().gta_dev_umma_probe(_ptr(A), _ptr(Bm), _ptr(P), _ptr(V), D, int(p_in_tmem), _ptr(outS),
+                                                         _ptr(outO), _stream(A.device)), "gta_dev_umma_probe")
     return outS, outO
+
+
+def pipeline_of(q, k, v, reps: PackedReps, f_dims: dict, *, flags: int = 0, euclid: bool = False) -> str:
+    """Name of the pipeline gta_attn_fwd selects for this call (gta_attn_fwd_pipeline)."""
+    dummy = torch.empty(16, device=q.device, dtype=q.dtype)
+    p = _params(q, k, v, dummy, reps, f_dims, None, 1.0, True, flags, euclid=euclid)
+    return _lib.GTA_PIPELINE_NAMES.get(lib().gta_attn_fwd_pipeline(p), "?")

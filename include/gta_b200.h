@@ -96,16 +96,18 @@ typedef struct GtaAttnParams {
  *                  key columns holding -0.5*|k'|^2 (hi + residual), head dim padded by 32.  Needs the larger workspace
  *                  reported by gta_attn_fwd_workspace_bytes_p. */
 
-#define GTA_FLAG_P_IN_TMEM 1   /* (v0 pipeline only) P operand of the PV MMA read from tensor memory */
 #define GTA_FLAG_SKIP_STAGE 2  /* workspace already holds K'/V' of these inputs: launch only the attention kernel */
 #define GTA_FLAG_STAGE_ONLY 4  /* launch only the K'/V' staging kernel (fills the workspace) */
 #define GTA_FLAG_FAST_FP32 128 /* fp32 inputs: multiply in plain bf16 (1e-2 budget) instead of the split-precision path */
-#define GTA_FLAG_V0_PIPELINE 8 /* first-generation kernel: one query tile per CTA, single softmax warpgroup */
 #define GTA_FLAG_V1_PIPELINE 16 /* second generation: two query tiles per CTA, non-persistent (default for D = 128) */
-#define GTA_FLAG_SINGLE_LAUNCH 32 /* ONE launch for K/V rotation + attention (gta_attn_fwd4.cu): the rotation is done by staging warps of
-                                   the persistent attention kernel itself, K'/V' tile images go through L2 with per-tile ready
-                                   flags.  bf16 / fast-fp32 inputs, D <= 96.  Measured 2-3 % slower than the default two-launch
-                                   pipeline (staging kernel + attention kernel) at 0.89x its DRAM traffic, see DESIGN.md */
+/* Pipeline selection for bf16 / fast-fp32 calls with D <= 96.  With neither bit set the library chooses from the shape
+ * (gta_attn_fwd_pipeline reports the choice): ONE launch unless the call is large AND rotation-heavy — 2*Tk/Tq > 1 key
+ * tiles to rotate per work item and more than 1e11 attention FLOPs — where the staging warps of the single-launch kernel
+ * cannot keep up with the tensor pipe and the stand-alone staging kernel wins by 2 % (measurements in DESIGN.md). */
+#define GTA_FLAG_SINGLE_LAUNCH 32 /* force ONE launch for K/V rotation + attention (gta_attn_fwd4.cu): the rotation is done by staging
+                                   warps of the persistent attention kernel itself, K'/V' tile images go through L2 with per-tile
+                                   ready flags; 0.89x the DRAM traffic of the two-launch pipeline */
+#define GTA_FLAG_TWO_LAUNCH 1024 /* force the two-launch pipeline: K'/V' staging kernel + persistent attention kernel */
 #define GTA_FLAG_V4_PIPELINE 256 /* two launches with the streaming-softmax / epilogue-warpgroup attention kernel (gta_attn_fwd5.cuh);
                                     head layouts without an instantiation fall back to the gta_attn_fwd3.cu kernel */
 #define GTA_FLAG_V5_PIPELINE 512 /* two launches; attention kernel with the spare P buffer in tensor memory (gta_attn_fwd6.cu): QK_X(j+1) is
@@ -124,6 +126,13 @@ size_t gta_attn_fwd_workspace_bytes_p(const GtaAttnParams* p);
 
 /* Fused forward: O = rho_q^{-1} softmax((rho_q^{-T} Q)(rho_k K)^T * scale) (rho_k V). */
 int gta_attn_fwd(const GtaAttnParams* p, void* stream);
+
+/* Which pipeline gta_attn_fwd runs for *p (workspace fields are ignored). */
+#define GTA_PIPELINE_TWO_LAUNCH 0      /* rotate_kv_kernel + attention kernel */
+#define GTA_PIPELINE_SINGLE_LAUNCH 1   /* attn_fwd4_kernel: rotation + attention in one launch */
+#define GTA_PIPELINE_SPLIT_PRECISION 2 /* fp32 inputs: staging + attn_fwd_hp_kernel */
+#define GTA_PIPELINE_GENERIC 3         /* t2 / euclid_sim / unaligned blocks: element-wise rep kernels around the attention */
+int gta_attn_fwd_pipeline(const GtaAttnParams* p);
 
 /* Backward of gta_attn_fwd (what torch.autograd derives from source/utils/gta.py:92-279 + source/layers.py:207-211 in
  * the reference's training step, source/trainer.py:69-83): gradients w.r.t. q, k, v and the layer's trans_coeff
@@ -180,19 +189,6 @@ int gta_so2_mats(const float* coord, int64_t n, int nfreqs, float max_freq_h, fl
 
 /* R [n,3,3] -> d1 [n,3,3], d2 [n,5,5] (ZYZ Euler angles with gimbal handling, D_l = Z J Z J Z). */
 int gta_wigner_d(const float* R, int64_t n, float* d1, float* d2, void* stream);
-
-/* tcgen05 self-test used by tests/test_umma_probe.py: S = A B^T (A,B [128,D] bf16 row-major) and
- * O = P V (P [128,128] bf16, V [128,D] bf16) through the same descriptor helpers as gta_attn_fwd.
- * outS [128,128], outO [128,D] fp32.  p_in_tmem selects the TS form for the PV product. */
-int gta_umma_probe(const void* A, const void* Bm, const void* P, const void* V, int D, int p_in_tmem,
-                   float* outS, float* outO, void* stream);
-
-/* tcgen05.mma issue/throughput micro-benchmark (tools/umma_bench.py): out[grid][2] = clocks (issue, issue+drain). */
-int gta_umma_bench(int D, int mode, int reps, int grid, long long* out, void* stream);
-
-/* exp2/pack phase micro-benchmark (tools/softmax_bench.py): clk[grid] = clocks of `reps` 128-column rows per thread. */
-int gta_softmax_bench(int num, int den, int warps, int reps, int grid, const float* in, float* out, long long* clk,
-                      void* stream);
 
 const char* gta_last_error(void);
 int gta_abi_version(void);

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     l = _lib.lib()
     for name in _declared_symbols():
         assert hasattr(l, name), name
-    assert l.gta_abi_version() == 3
+    assert l.gta_abi_version() == 4
 
 
 def test_struct_layout_matches_header_order():
@@ -82,9 +82,11 @@ def test_backward_and_probs_argument_validation():
 
 def test_workspace_bytes():
     l = _lib.lib()
-    # 2 tensors x B*H x ceil(Tk/128) tiles x 128*D*2 bytes
-    assert l.gta_attn_fwd_workspace_bytes(2, 8, 1280, 96) == 2 * 2 * 8 * 10 * 128 * 96 * 2
-    assert l.gta_attn_fwd_workspace_bytes(1, 6, 600, 64) == 2 * 6 * 5 * 128 * 64 * 2
+    # 2 tensors x B*H x ceil(Tk/128) tiles x 128*D*2 bytes + one ready flag (int) per tile for the single-launch kernel,
+    # rounded up to 1 KiB
+    flags = lambda units: (units * 4 + 1023) // 1024 * 1024
+    assert l.gta_attn_fwd_workspace_bytes(2, 8, 1280, 96) == 2 * 2 * 8 * 10 * 128 * 96 * 2 + flags(2 * 8 * 10)
+    assert l.gta_attn_fwd_workspace_bytes(1, 6, 600, 64) == 2 * 6 * 5 * 128 * 64 * 2 + flags(6 * 5)
     assert l.gta_attn_fwd_workspace_bytes(0, 6, 600, 64) == 0
     p = _params(B=2, H=8, Tk=1280, Tq=1280, D=96, se3=48, so3=24, so2=24)
     assert l.gta_attn_fwd_workspace_bytes_p(ctypes.byref(p)) == l.gta_attn_fwd_workspace_bytes(2, 8, 1280, 96)
@@ -92,6 +94,40 @@ def test_workspace_bytes():
     g = _params(B=1, H=6, Tq=600, Tk=600, D=64, triv=2, se3=32, so3=0, so2=0, t2=30)
     dense = 3 * ((6 * 600 * 64 * 2 + 1023) // 1024 * 1024) + (6 * 600 * 64 * 4 + 1023) // 1024 * 1024
     assert l.gta_attn_fwd_workspace_bytes_p(ctypes.byref(g)) == dense + l.gta_attn_fwd_workspace_bytes(1, 6, 600, 64)
+
+
+def test_pipeline_selection():
+    """gta_attn_fwd_pipeline: the shape rule and the forcing flags (no CUDA work)."""
+    l = _lib.lib()
+    msn_enc = _params(B=64, H=8, Tk=1280, Tq=1280, D=96, se3=48, so3=24, so2=24)
+    msn_dec = _params(B=64, H=8, Tk=1280, Tq=2560, D=96, se3=48, so3=24, so2=24)
+    clevr = _params(B=32, H=6, Tk=600, Tq=600, D=64, se3=32, so3=0, so2=32)
+    assert l.gta_attn_fwd_pipeline(ctypes.byref(msn_enc)) == 0      # large and rotation-heavy: staging kernel + attention kernel
+    assert l.gta_attn_fwd_pipeline(ctypes.byref(msn_dec)) == 1      # one key tile to rotate per work item: one launch
+    assert l.gta_attn_fwd_pipeline(ctypes.byref(clevr)) == 1        # small: one launch
+    msn_enc.flags = _lib.GTA_FLAG_SINGLE_LAUNCH
+    assert l.gta_attn_fwd_pipeline(ctypes.byref(msn_enc)) == 1
+    clevr.flags = _lib.GTA_FLAG_TWO_LAUNCH
+    assert l.gta_attn_fwd_pipeline(ctypes.byref(clevr)) == 0
+    f32 = _params(B=2, H=6, Tk=600, Tq=600, D=64, se3=32, so3=0, so2=32, in_dtype=_lib.GTA_DTYPE_F32)
+    assert l.gta_attn_fwd_pipeline(ctypes.byref(f32)) == 2
+    f32.flags = _lib.GTA_FLAG_FAST_FP32
+    assert l.gta_attn_fwd_pipeline(ctypes.byref(f32)) == 1
+    t2 = _params(B=1, H=6, Tq=600, Tk=600, D=64, triv=2, se3=32, so3=0, so2=0, t2=30)
+    assert l.gta_attn_fwd_pipeline(ctypes.byref(t2)) == 3
+
+
+def test_dev_library_is_separate():
+    """Probes, micro-benchmarks and the first-generation kernel live in libgta_b200_dev.so, not in the product ABI."""
+    d = _lib.dev_lib()
+    for name in _lib.DEV_SYMBOLS:
+        assert hasattr(d, name), name
+    prod = _lib.lib()
+    for name in ("gta_umma_probe", "gta_umma_bench", "gta_softmax_bench", "gta_dev_umma_probe"):
+        assert not hasattr(prod, name), name
+    txt = open(os.path.join(ROOT, "include", "gta_b200_dev.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    assert sorted(set(re.findall(r"\b(gta_dev_[a-z0-9_]+)\s*\(", txt))) == sorted(_lib.DEV_SYMBOLS)
 
 
 def _params(**over):

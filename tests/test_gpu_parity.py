@@ -24,7 +24,7 @@ FP32_TOL = 1e-3
 # GTA_FLAG_* pipeline selectors of the product library: the default two-launch pipeline (staging kernel + persistent
 # attention kernel), the single-launch pipeline (K/V rotation by staging warps of the attention kernel), the
 # streaming-softmax / epilogue-warpgroup kernel, the spare-P-buffer kernel, V1 (non-persistent two-tile)
-PIPELINES, PIPELINE_IDS = [0, 32, 256, 512, 16], ["v2_two_launch", "v3_single_launch", "v4_streaming", "v5_spare_p", "v1"]
+PIPELINES, PIPELINE_IDS = [1024, 32, 256, 512, 16, 0], ["v2_two_launch", "v3_single_launch", "v4_streaming", "v5_spare_p", "v1", "auto"]
 
 
 def _ops():

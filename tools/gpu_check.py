@@ -102,7 +102,7 @@ def _attn(base, args, dt, flags, tc=0.01, vt=True):
 def step_attn_small():
     import torch
     from gta_b200.synth import CFG1_A, CFG1_B, CLEVR, MSN_SO3
-    for flags in (0, 8):
+    for flags in (0, 16):
         _attn(CFG1_A, (2, 2, 64, 64, False, 1), torch.bfloat16, flags)           # exactly one tile
         _attn(CFG1_B, (2, 2, 16, 16, False, 2), torch.float32, flags)            # partial tile
         _attn(MSN_SO3, (5, 5, 64, 64, False, 1), torch.bfloat16, flags)          # 320 tokens: 3 tiles, tail 64
@@ -112,7 +112,7 @@ def step_attn_small():
 def step_attn_shapes():
     import torch
     from gta_b200.synth import CLEVR, MSN_SO3
-    for flags in (0, 8):
+    for flags in (0, 16):
         _attn(MSN_SO3, (5, 5, 256, 256, False, 1), torch.bfloat16, flags)
         _attn(MSN_SO3, (5, 5, 512, 256, True, 1), torch.bfloat16, flags)
         _attn(CLEVR, (2, 2, 300, 300, False, 2), torch.bfloat16, flags)

@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import torch
 from gta_b200 import _lib
 
-l = _lib.lib()
+l = _lib.dev_lib()
 names = {0: "QK SS N=128 (D/16 MMAs)", 1: "QK SS N=64 (D/16 MMAs)", 2: "PV TS N=D (8 MMAs)", 3: "PV SS N=D (8 MMAs)",
          4: "PV TS N=D (4 MMAs)"}
 for D in (96, 64, 128):
@@ -14,7 +14,7 @@ for D in (96, 64, 128):
             reps = 200
             out = torch.zeros(grid, 2, dtype=torch.int64, device="cuda")
             for _ in range(2):
-                _lib.check(l.gta_umma_bench(D, mode, reps, grid, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+                _lib.check_dev(l.gta_dev_umma_bench(D, mode, reps, grid, out.data_ptr(), torch.cuda.current_stream().cuda_stream))
             torch.cuda.synchronize()
             o = out.double().cpu()
             nm = (D // 16) if mode < 2 else (8 if mode < 4 else 4)
