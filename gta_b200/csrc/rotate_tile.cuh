@@ -52,23 +52,32 @@ __device__ __forceinline__ void rotate_tile(const RotArgs& a, const int tile, co
     uint8_t* kdst = a.ws_k + blob * tile_bytes;
     uint8_t* vdst = a.ws_v + blob * tile_bytes;
 
+    // view of a row without a division per item: tile rows are consecutive tokens, and with at least 128 tokens per view
+    // (every model shape) a tile crosses at most one view boundary
+    const int t0 = tile * 128;
+    const int view0 = t0 / a.tpv, rem0 = t0 - view0 * a.tpv;
+    const bool one_boundary = a.tpv >= 128;
+
     int cbase = 0;
 #pragma unroll 1
     for (int seg = 0; seg < 4; ++seg) {
         const int n_t = seg_n[seg];
         if (n_t == 0) continue;
-        // this warp's items of the segment: (row r, chunk cbase + c), item index it = r * n_t + c, it in [0, 32 n_t)
+        // this warp's items of the segment: (row r, chunk cbase + c), item index it = r * n_t + c, it in [0, 32 n_t); lane l
+        // holds items l, l + 32, ...: (r, c) advance by (32 / n_t, 32 % n_t) with a carry instead of a division per item
+        const int q32 = 32 / n_t, m32 = 32 - q32 * n_t;
+        int r_it = lane / n_t, c_it = lane - r_it * n_t;
 #pragma unroll 1
         for (int base = 0; base < n_t; base += kRotUnroll) {
             RawChunk<T> rk[kRotUnroll], rv[kRotUnroll];
             int row[kRotUnroll], ch[kRotUnroll];
 #pragma unroll
             for (int u = 0; u < kRotUnroll; ++u) {
-                const int it = (base + u) * 32 + lane;
-                const int r = it / n_t;
-                ch[u] = cbase + (it - r * n_t);
-                row[u] = (base + u < n_t) ? warp * 32 + r : -1;
-                const int t = tile * 128 + row[u];
+                ch[u] = cbase + c_it;
+                row[u] = (base + u < n_t) ? warp * 32 + r_it : -1;
+                c_it += m32; r_it += q32;
+                if (c_it >= n_t) { c_it -= n_t; ++r_it; }
+                const int t = t0 + row[u];
                 zero_raw(rk[u]); zero_raw(rv[u]);
                 if (row[u] >= 0 && t < a.Tk) {
                     load_raw(ksrc + t * a.k_st + ch[u] * 8, rk[u]);
@@ -78,12 +87,13 @@ __device__ __forceinline__ void rotate_tile(const RotArgs& a, const int tile, co
 #pragma unroll
             for (int u = 0; u < kRotUnroll; ++u) {
                 if (row[u] < 0) continue;
-                const int t = tile * 128 + row[u];
+                const int t = t0 + row[u];
                 float xk[8], xv[8];
                 raw_to_f32(rk[u], xk);
                 raw_to_f32(rv[u], xv);
                 if (seg > 0 && t < a.Tk) {
-                    const size_t view = static_cast<size_t>(b) * a.Nk + t / a.tpv;
+                    const int vrow = one_boundary ? view0 + (rem0 + row[u] >= a.tpv ? 1 : 0) : t / a.tpv;
+                    const size_t view = static_cast<size_t>(b) * a.Nk + vrow;
                     const float* se3 = a.se3_k + view * 16;
                     const float* so3 = a.so3_k + view * 34;
                     const float* so2 = a.so2_k + (static_cast<size_t>(b) * a.Tk + t) * a.C * 2;
