@@ -1,11 +1,32 @@
 // Pieces shared by the attention kernels: UMMA descriptors of the operand tile images and the kernel arguments.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "reps.cuh"
 
 namespace gta {
 
 constexpr uint32_t kTmemCols = 512;
+
+// Head layout [triv | se3 | so3 | so2] as a compile-time parameter (straight-line rep code for the shipped configs).
+template <int TRIV, int SE3, int SO3, int SO2>
+struct HeadLayout {
+    static constexpr int kTriv = TRIV, kSe3 = SE3, kSo3 = SO3, kSo2 = SO2;
+    static constexpr int D = TRIV + SE3 + SO3 + SO2;
+    static constexpr int c1 = TRIV / 8, c2 = c1 + SE3 / 8, c3 = c2 + SO3 / 8, c4 = c3 + SO2 / 8;   // chunk boundaries
+    static_assert(TRIV % 8 == 0 && SE3 % 8 == 0 && SO3 % 8 == 0 && SO2 % 8 == 0, "blocks are whole 16-byte chunks");
+};
+
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+
 
 // K-step kk (16 elements of the head dim) of a K-major operand tile (Q' or K'), 64B swizzle:
 // 8-row groups are 512 B apart (SBO); inside a 64-byte row the step advances the start address by 32 B.

@@ -1,763 +1,17 @@
-// Fused GTA attention forward, v3 pipeline: ONE launch for K/V rotation + attention.
-//
-// Same persistent two-tile tensor-core pipeline as gta_attn_fwd3.cu (one CTA per SM; work item = (batch, head, 256 query
-// rows); tcgen05 QK^T / PV with TMEM accumulators, online softmax by two warpgroups, K'/V' tile images fetched by bulk
-// async copies), plus a fourth warpgroup of STAGING warps that does all rep rotation that is not on the softmax path:
-//
-//   warps 0-3 / 4-7   softmax warpgroup A / B (+ epilogue: O/l, rho_q^{-1}, stores)            184 registers
-//   warp  8           UMMA issuer (one elected lane)                                            56 registers
-//   warp  9           bulk-copy producer: waits for the K'/V' tiles' ready flags, then cp.async.bulk
-//   warps 10-11       idle (they only complete the warpgroup for setmaxnreg)
-//   warps 12-15       staging warps                                                             88 registers
-//                       * K' = rho_k K, V' = rho_k V of whole 128-key tiles ("units"), written as UMMA operand tile
-//                         images to the workspace in global memory (they stay L2-resident: a unit is consumed by the
-//                         Tq/256 work items of its (batch, head) within the next round) and published with a
-//                         release store of the unit's ready flag
-//                       * Q' = rho_q^{-T} Q of the NEXT work item into the double-buffered shared-memory Q area
-//
-// Rotation schedule.  Items are dealt round-robin (CTA c takes items c, c+G, ...; round r = items [rG, (r+1)G)); units
-// u = (b*H + h)*ntiles + j are dealt round-robin too (CTA c rotates u = c, c+G, ...).  In iteration r the staging warps
-// of every CTA rotate their units below Uneed(r) = (last (b,h) touched by round r + 1) * ntiles and then stage Q' of
-// their round-r item; the double-buffered Q area lets them run one item ahead of the tensor pipe, so the units of round r
-// are produced while round r-1 computes.  Staging warps never wait on another CTA, and every wait of a CTA depends
-// only on work of strictly earlier iterations, so the grid cannot deadlock as long as its CTAs are co-resident
-// (grid <= number of SMs, one CTA per SM; checked on the host).
-//
-// Cross-CTA visibility of a unit: staging threads st.global the tile images, fence.proxy.async (the consumer reads them
-// through the async proxy), bar.sync among the 128 staging threads, then one thread __threadfence() + st.release.gpu
-// flag.  The producer lane ld.acquire.gpu's the flags of its item's (b,h), fence.proxy.async, then issues the copies.
-// Flags are zeroed by a cudaMemsetAsync in front of the launch (U = B*H*ntiles ints).
-//
-// Reference semantics: source/utils/gta.py:92-279 and source/layers.py:202-211.
-#include <cmath>
-
-#include "attn_common.cuh"
-#include "rotate_tile.cuh"
+// Single-launch forward (gta_attn_fwd4.cuh): instantiations with the head layout taken from the call at run time, and the
+// dispatcher.  gta_attn_fwd4_ct.cu holds the instantiations specialised for the shipped layouts.
+#include "gta_attn_fwd4.cuh"
 
 namespace gta {
 
-constexpr int kThreads4 = 512;
-// Register split (setmaxnreg; 2 * kRegSoftmax + kRegIssue + kRegStage = 512 = 65 536 / 128 threads per warpgroup)
-#ifndef GTA_REG_SOFTMAX
-#define GTA_REG_SOFTMAX 184
-#endif
-#ifndef GTA_REG_ISSUE
-#define GTA_REG_ISSUE 56
-#endif
-#ifndef GTA_REG_STAGE
-#define GTA_REG_STAGE 88
-#endif
-static_assert(2 * GTA_REG_SOFTMAX + GTA_REG_ISSUE + GTA_REG_STAGE <= 512, "register split exceeds the register file");
-constexpr int kStagerThreads4 = 128;
-#ifndef GTA_QSTAGE_WARPS
-#define GTA_QSTAGE_WARPS 0
-#endif
-constexpr int kQWarps = GTA_QSTAGE_WARPS;     // 2: Q' staged by warps 10-11 (own loop); 0: by the K'/V' staging warps 12-15
-#ifndef GTA_KV_BATCH
-#define GTA_KV_BATCH 3
-#endif
-#ifndef GTA_Q_BATCH
-#define GTA_Q_BATCH 6
-#endif
-#ifndef GTA_PF_UNITS
-#define GTA_PF_UNITS 2
-#endif
-constexpr int kPfUnits = GTA_PF_UNITS;        // L2 prefetch distance of the raw K/V rows, in units of this CTA
-constexpr uint32_t k4TmemSA = 0, k4TmemSB = 128, k4TmemOA = 256, k4TmemOB = 384;
-constexpr float k4RescaleThreshold = 8.0f;   // log2 units
-// Fraction of the exponentials evaluated with poly_exp2x2 instead of MUFU.EX2: pairs with (i % DEN) < NUM.
-#ifndef GTA_POLY_NUM
-#define GTA_POLY_NUM 0
-#endif
-#ifndef GTA_POLY_DEN
-#define GTA_POLY_DEN 4
-#endif
-
-template <int D>
-struct Attn4Cfg {
-    static constexpr int kStages = 2;
-    static constexpr uint32_t kTile = 128u * D * 2u;
-    static constexpr uint32_t kQ = 0;                          // [2 buffers][2 tiles]
-    static constexpr uint32_t kK = 4 * kTile;                  // [kStages]
-    static constexpr uint32_t kV = kTile * (4 + kStages);      // [kStages]
-    static constexpr uint32_t kBars = kTile * (4 + 2 * kStages);
-    enum : int {
-        bQFull = 0,                        // [buf][X]  count 128 (stager threads)
-        bQFree = 4,                        // [buf][X]  tcgen05.commit after the item's last QK_X
-        bKFull = 8,                        // [kStages]
-        bVFull = bKFull + kStages,
-        bKEmpty = bVFull + kStages,
-        bVEmpty = bKEmpty + kStages,
-        bSFull = bVEmpty + kStages,        // [X] commit
-        bPFull = bSFull + 2,               // [X] count 128
-        bOFinal = bPFull + 2,              // [X] commit after the item's last PV_X
-        bOFree = bOFinal + 2,              // [X] count 128: O_X drained to registers
-        bCount = bOFree + 2
-    };
-    static constexpr uint32_t kTmemSlot = kBars + bCount * 8;
-    static constexpr uint32_t kUsed = kTmemSlot + 16;
-    static constexpr uint32_t kBytes = (kUsed + 1024 > 120u * 1024u) ? kUsed + 1024 : 120u * 1024u;
-};
-
-struct ItemCoord4 {
-    int b, h, p;
-    bool has_b;
-};
-__device__ __forceinline__ ItemCoord4 decode_item4(int item, int npairs, int H, int Tq) {
-    ItemCoord4 c;
-    c.p = item % npairs;
-    const int bh = item / npairs;
-    c.h = bh % H;
-    c.b = bh / H;
-    c.has_b = (c.p * 256 + 128) < Tq;
-    return c;
-}
-
-struct Fused4Args {
-    RotArgs rot;        // K/V side of the rotation (strides, k-side rep tables, workspace tile images)
-    int* flags;         // [B*H*ntiles] unit ready flags (zeroed before the launch); nullptr: workspace is pre-staged
-    int nunits;         // B*H*ntiles
-};
-
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_gpu(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_global() {
-    asm volatile("fence.proxy.async.global;" ::: "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// One unit = one 128-key tile of one (batch, head): K' = rho_k K and V' = rho_k V, one key row per staging thread.  The row
-// is walked in batches of kCB 16-byte chunks of K and of V (all loads of a batch in flight before the first use; K and
-// V share the token's rep data) and written as UMMA operand tile images.
-template <typename TIn, int D>
-__device__ __forceinline__ void stage_kv_unit(const RotArgs& ra, const int tile, const int h, const int b, const int row,
-                                              const float tc) {
-    constexpr int kCB = (sizeof(TIn) == 2) ? GTA_KV_BATCH : 2;     // chunks of K and of V per batch (8 registers of raw data each)
-    const int t = tile * 128 + row;
-    const bool valid = t < ra.Tk;
-    const int tt = valid ? t : ra.Tk - 1;
-    const TIn* krow = reinterpret_cast<const TIn*>(ra.k) + static_cast<int64_t>(b) * ra.k_sb + static_cast<int64_t>(h) * ra.k_sh +
-                      static_cast<int64_t>(tt) * ra.k_st;
-    const TIn* vrow = reinterpret_cast<const TIn*>(ra.v) + static_cast<int64_t>(b) * ra.v_sb + static_cast<int64_t>(h) * ra.v_sh +
-                      static_cast<int64_t>(tt) * ra.v_st;
-    const size_t view = static_cast<size_t>(b) * ra.Nk + tt / ra.tpv;
-    const float* se3 = ra.se3_k + view * 16;
-    const float* so3 = ra.so3_k + view * 34;
-    const float* so2 = ra.so2_k + (static_cast<size_t>(b) * ra.Tk + tt) * ra.C * 2;
-    const size_t blob = (static_cast<size_t>(b) * ra.H + h) * ra.ntiles + tile;
-    uint8_t* kdst = ra.ws_k + blob * (static_cast<size_t>(128) * D * 2);
-    uint8_t* vdst = ra.ws_v + blob * (static_cast<size_t>(128) * D * 2);
-    stage_row<TIn, kModeKV, true, kCB>(krow, vrow, valid, ra.v_transform != 0, ra.hd, se3, so3, so2, tc,
-                                        [&](int c, const float* xk, const float* xv) {
-                                            const uint32_t off = tile_sw64_offset(row, c);
-                                            *reinterpret_cast<uint4*>(kdst + off) = pack_chunk_bf16(xk);
-                                            *reinterpret_cast<uint4*>(vdst + off) = pack_chunk_bf16(xv);
-                                        });
-}
-// Pull the raw K / V rows of a unit into L2 ahead of their use (one row per staging thread; a row of D elements spans at
-// most two or three 128-byte lines).
-template <typename TIn, int D>
-__device__ __forceinline__ void prefetch_row(const TIn* row) {
-    constexpr int kBytes = D * sizeof(TIn);
-    const char* p = reinterpret_cast<const char*>(row);
-#pragma unroll
-    for (int o = 0; o < kBytes; o += 128) prefetch_l2(p + o);
-    if ((reinterpret_cast<uintptr_t>(p) & 127) + (kBytes & 127 ? (kBytes & 127) : 128) > 128) prefetch_l2(p + kBytes - 16);
-}
-template <typename TIn, int D>
-__device__ __forceinline__ void prefetch_kv_unit(const RotArgs& ra, const int tile, const int h, const int b, const int row) {
-    const int t = tile * 128 + row;
-    if (t >= ra.Tk) return;
-    prefetch_row<TIn, D>(reinterpret_cast<const TIn*>(ra.k) + static_cast<int64_t>(b) * ra.k_sb + static_cast<int64_t>(h) * ra.k_sh +
-                         static_cast<int64_t>(t) * ra.k_st);
-    prefetch_row<TIn, D>(reinterpret_cast<const TIn*>(ra.v) + static_cast<int64_t>(b) * ra.v_sb + static_cast<int64_t>(h) * ra.v_sh +
-                         static_cast<int64_t>(t) * ra.v_st);
-}
-
-// kDbg: phase clocks into AttnArgs.dbg (tools/phase_timing*.py); compiled out of the production instantiation.
-template <typename TIn, typename TOut, int D, bool kDbg>
-__global__ void __launch_bounds__(kThreads4, 1) attn_fwd4_kernel(const AttnArgs a, const Fused4Args f, const int npairs,
-                                                                 const int nitems) {
-    using L = Attn4Cfg<D>;
-    constexpr int NS = L::kStages;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = a.ntiles_k;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(&bars[L::bQFull + i], kQWarps ? 64 : kStagerThreads4);
-            mbar_init(&bars[L::bQFree + i], 1);
-        }
-        for (int x = 0; x < 2; ++x) {
-            mbar_init(&bars[L::bSFull + x], 1);
-            mbar_init(&bars[L::bPFull + x], 128);
-            mbar_init(&bars[L::bOFinal + x], 1);
-            mbar_init(&bars[L::bOFree + x], 128);
-        }
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(&bars[L::bKFull + s], 1);
-            mbar_init(&bars[L::bVFull + s], 1);
-            mbar_init(&bars[L::bKEmpty + s], 1);
-            mbar_init(&bars[L::bVEmpty + s], 1);
-        }
-        fence_mbar_init();
-    }
-    if (warp == 8) {
-        tmem_alloc(tmem_slot, kTmemCols);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const float tc = a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f;
-
-    // Q' = rho_q^{-T} Q of row r of tile X of an item into the operand tile at sQ
-    auto stage_q_row = [&](const ItemCoord4& ic, const int X, uint8_t* sQ, const int r) {
-        const int t = ic.p * 256 + X * 128 + r;
-        const bool valid = t < a.Tq;
-        const int tt = valid ? t : a.Tq - 1;
-        const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
-        const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
-        const TIn* qrow = reinterpret_cast<const TIn*>(a.q) + static_cast<int64_t>(ic.b) * a.q_sb +
-                          static_cast<int64_t>(ic.h) * a.q_sh + static_cast<int64_t>(tt) * a.q_st;
-        const float* se3 = a.se3_q + view * 16;
-        const float* so3 = a.so3_q + view * 34;
-        constexpr int kQB = (sizeof(TIn) == 2) ? GTA_Q_BATCH : 4;      // chunks per batch (4 registers of raw data each)
-        stage_row<TIn, kModeQ, false, kQB>(qrow, qrow, valid, false, a.hd, se3, so3, so2, tc,
-                                           [&](int c, const float* x, const float*) {
-                                               *reinterpret_cast<uint4*>(sQ + tile_sw64_offset(r, c)) = pack_chunk_bf16(x);
-                                           });
-    };
-    auto prefetch_q_row = [&](const ItemCoord4& ic, const int X, const int r) {
-        const int t = ic.p * 256 + X * 128 + r;
-        if (t < a.Tq)
-            prefetch_row<TIn, D>(reinterpret_cast<const TIn*>(a.q) + static_cast<int64_t>(ic.b) * a.q_sb +
-                                 static_cast<int64_t>(ic.h) * a.q_sh + static_cast<int64_t>(t) * a.q_st);
-    };
-
-    if (warp < 8) {
-        // =========================================================== softmax warpgroups (+ epilogue)
-        setmaxnreg_inc<GTA_REG_SOFTMAX>();
-        const int X = warp >> 2;
-        const int r = threadIdx.x & 127;
-        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-        const uint32_t s_addr = lane_base + (X ? k4TmemSB : k4TmemSA);
-        const uint32_t o_addr = lane_base + (X ? k4TmemOB : k4TmemOA);
-        const float cs = a.scale_log2;
-        const uint64_t cs2 = pack_f32x2(cs, cs);
-        uint32_t gt = 0;      // tiles processed by this warpgroup (s_full / p_full phase)
-        uint32_t cnt = 0;     // items processed by this warpgroup (o_final phase)
-        // optional phase clocks (GtaAttnParams.debug_clocks): [cta][16] accumulated over the CTA's items
-        long long* dbg = (kDbg && a.dbg && threadIdx.x == 0) ? a.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
-        long long d_loop = 0, d_epi = 0, d_wait_s = 0, d_wait_o = 0, d_items = 0;
-        long long d_e[4] = {0, 0, 0, 0};
-        const long long d_start = dbg ? clock64() : 0;
-
-#pragma unroll 1
-        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const ItemCoord4 ic = decode_item4(item, npairs, a.H, a.Tq);
-            if (X == 1 && !ic.has_b) continue;
-            float m_used = -INFINITY, l_run = 0.f;
-            const long long d_t0 = dbg ? clock64() : 0;
-
-#pragma unroll 1
-            for (int j = 0; j < n; ++j, ++gt) {
-                if (j == n - 1 && a.v_transform) {
-                    // pull this row's output-rotation operands into L1 one key tile before the epilogue needs them
-                    const int t_ = ic.p * 256 + X * 128 + r;
-                    const int tt_ = t_ < a.Tq ? t_ : a.Tq - 1;
-                    const size_t view_ = static_cast<size_t>(ic.b) * a.Nq + tt_ / a.tpvq;
-                    if (a.hd.se3) prefetch_l1(a.se3_q + view_ * 16);
-                    if (a.hd.so3) { prefetch_l1(a.so3_q + view_ * 34); prefetch_l1(a.so3_q + view_ * 34 + 32); }
-                    if (a.hd.so2) {
-                        const float* so2_ = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt_) * a.C * 2;
-                        for (int off = 0; off < a.C * 2; off += 32) prefetch_l1(so2_ + off);
-                    }
-                }
-                const long long d_w0 = dbg ? clock64() : 0;
-                mbar_wait(&bars[L::bSFull + X], gt & 1);
-                if (dbg) d_wait_s += clock64() - d_w0;
-                tc_fence_after();
-                uint32_t sreg[128];
-                tmem_ld32(s_addr, sreg);
-                tmem_ld32(s_addr + 32, sreg + 32);
-                tmem_ld32(s_addr + 64, sreg + 64);
-                tmem_ld32(s_addr + 96, sreg + 96);
-                tmem_ld_wait();
-                float* s = reinterpret_cast<float*>(sreg);
-                if (j == n - 1) {
-                    const int nvalid = a.Tk - j * 128;
-                    if (nvalid < 128) {
-#pragma unroll
-                        for (int i = 0; i < 128; ++i) if (i >= nvalid) s[i] = -INFINITY;
-                    }
-                }
-                float mx0 = fmax3(s[0], s[1], s[2]), mx1 = fmax3(s[3], s[4], s[5]);
-                float mx2 = fmax3(s[6], s[7], s[8]), mx3 = fmax3(s[9], s[10], s[11]);
-#pragma unroll
-                for (int i = 12; i < 124; i += 8) {
-                    mx0 = fmax3(mx0, s[i], s[i + 1]); mx1 = fmax3(mx1, s[i + 2], s[i + 3]);
-                    mx2 = fmax3(mx2, s[i + 4], s[i + 5]); mx3 = fmax3(mx3, s[i + 6], s[i + 7]);
-                }
-                mx0 = fmax3(mx0, s[124], s[125]); mx1 = fmax3(mx1, s[126], s[127]);
-                const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-
-                const bool grow = (m_tile - m_used) * cs > k4RescaleThreshold;   // always true on the item's first tile
-                if (__any_sync(0xffffffffu, grow)) {
-                    const float m_new = grow ? m_tile : m_used;
-                    const float alpha = grow ? fast_exp2((m_used - m_new) * cs) : 1.0f;
-                    l_run *= alpha;
-                    m_used = m_new;
-                    if (j > 0) {
-#pragma unroll 1
-                        for (int c8 = 0; c8 < D / 8; ++c8) {      // rare: keep the footprint at 8 registers
-                            uint32_t o8[8];
-                            tmem_ld8(o_addr + c8 * 8, o8);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) o8[i] = __float_as_uint(__uint_as_float(o8[i]) * alpha);
-                            tmem_st8(o_addr + c8 * 8, o8);
-                        }
-                    }
-                }
-
-                const float neg = -m_used * cs;
-                const uint64_t neg2 = pack_f32x2(neg, neg);
-                uint64_t lsum2 = pack_f32x2(0.f, 0.f);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    // packed in place: P pair i overwrites sreg[half*64 + i] after s[half*64 + 2i], s[.. + 2i+1] were consumed,
-                    // so the store reuses the register block the load filled (no second 32-register block is needed)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const uint64_t x2 = ffma2(pack_f32x2(s[half * 64 + 2 * i], s[half * 64 + 2 * i + 1]), cs2, neg2);
-                        float p0, p1;
-                        if ((i % GTA_POLY_DEN) < GTA_POLY_NUM) {
-                            poly_exp2x2(x2, p0, p1);
-                        } else {
-                            float x0, x1;
-                            unpack_f32x2(x2, x0, x1);
-                            p0 = fast_exp2(x0); p1 = fast_exp2(x1);
-                        }
-                        lsum2 = fadd2(lsum2, pack_f32x2(p0, p1));
-                        sreg[half * 64 + i] = pack_bf16x2(p0, p1);
-                    }
-                    tmem_st32(s_addr + half * 32, sreg + half * 64);
-                }
-                float ls0, ls1;
-                unpack_f32x2(lsum2, ls0, ls1);
-                l_run += ls0 + ls1;
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(&bars[L::bPFull + X]);
-            }
-
-            // ---- epilogue of this item: prefetch the row's reps, drain O to registers, release O, then finish.
-            const long long d_t1 = dbg ? clock64() : 0;
-            const int t = ic.p * 256 + X * 128 + r;
-            const bool valid = t < a.Tq;
-            const int tt = valid ? t : a.Tq - 1;
-            // The output rotation walks the head row block type by block type with rolled loops (8 accumulator columns
-            // per step straight from TMEM), so only ONE kind of rep data is live at a time: the view matrices are requested
-            // before the wait for the last PV, the per-token SO(2) entries one chunk ahead of their use.  (A fully
-            // unrolled epilogue kept M, W and all SO(2) chunks live next to 96 accumulator values and spilled ~150
-            // local-memory loads per 32-column block.)
-            const int c_se3 = a.hd.triv >> 3, n_se3 = a.hd.se3 >> 3, c_so3 = c_se3 + n_se3, n_so3 = a.hd.so3 >> 3;
-            const int c_so2 = c_so3 + n_so3;
-            // (all of this row's rep data was pulled into L1 one key tile ago, so each block loads its operands right
-            //  before use and nothing has to stay live across the wait)
-            const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
-            const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
-            mbar_wait(&bars[L::bOFinal + X], cnt & 1);
-            const long long d_t2 = dbg ? clock64() : 0;
-            ++cnt;
-            tc_fence_after();
-            const float inv_l = 1.0f / l_run;
-            TOut* orow = reinterpret_cast<TOut*>(a.out) + ((static_cast<int64_t>(ic.b) * a.Tq + tt) * a.H + ic.h) * D;
-            // O columns are fetched 8 at a time, one chunk AHEAD of their use (tcgen05.ld is asynchronous until
-            // tcgen05.wait::ld), so the TMEM round trip overlaps the rotation of the previous chunk.
-            uint32_t ocur[8];
-            tmem_ld8(o_addr, ocur);
-            auto next_o = [&](int c, float* x) {          // returns chunk c (already in flight), starts chunk c + 1
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(ocur[i]) * inv_l;
-                if (c + 1 < D / 8) tmem_ld8(o_addr + (c + 1) * 8, ocur);   // consumed above; in-order issue makes the reuse safe
-            };
-            // 32-byte stores (STG.256): a thread owns a whole 2*D-byte output row, so every 16-byte store is its own
-            // L1/L2 transaction (the v2 epilogue was bound by ~2.5 clk per such transaction); pairing two chunks halves
-            // the transaction count and writes full sectors.  `pend` carries the even chunk across block-type sections.
-            uint4 pend = make_uint4(0, 0, 0, 0);
-            auto emit = [&](int c, const float* x) {
-                if (sizeof(TOut) == 4) {
-                    if (valid)
-                        st_global_v8(orow + c * 8, make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])),
-                                     make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7])));
-                } else {
-                    const uint4 pk = pack_chunk_bf16(x);
-                    if (c & 1) { if (valid) st_global_v8(orow + (c - 1) * 8, pend, pk); }
-                    else pend = pk;
-                }
-            };
-            const long long e0 = dbg ? clock64() : 0;
-            const int c_rot = a.v_transform ? c_se3 : D / 8;       // chunks below c_rot are stored as they are
-#pragma unroll 1
-            for (int c = 0; c < c_rot; ++c) {
-                float x[8];
-                next_o(c, x);
-                emit(c, x);
-            }
-            long long e1 = 0, e2 = 0;
-            if (a.v_transform) {
-                if (c_so3 > c_se3) {
-                    float M[16];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 q4 = __ldg(reinterpret_cast<const float4*>(a.se3_q + view * 16) + i);
-                        M[4 * i] = q4.x; M[4 * i + 1] = q4.y; M[4 * i + 2] = q4.z; M[4 * i + 3] = q4.w;
-                    }
-#pragma unroll 1
-                    for (int c = c_se3; c < c_so3; ++c) {
-                        float x[8];
-                        next_o(c, x);
-                        se3_apply(x, M, tc);
-                        emit(c, x);
-                    }
-                }
-                if (dbg) e1 = clock64();
-                if (c_so2 > c_so3) {
-                    float W[34];
-#pragma unroll
-                    for (int i = 0; i < 17; ++i) {
-                        const float2 q2 = __ldg(reinterpret_cast<const float2*>(a.so3_q + view * 34) + i);
-                        W[2 * i] = q2.x; W[2 * i + 1] = q2.y;
-                    }
-#pragma unroll 1
-                    for (int c = c_so3; c < c_so2; ++c) {
-                        float x[8];
-                        next_o(c, x);
-                        so3_apply<true>(x, W);
-                        emit(c, x);
-                    }
-                }
-                if (dbg) e2 = clock64();
-                So2Chunk sc_cur = load_so2_chunk(so2, c_so2, a.hd);
-#pragma unroll 1
-                for (int c = c_so2; c < D / 8; ++c) {
-                    So2Chunk sc_nxt = sc_cur;
-                    if (c + 1 < D / 8) sc_nxt = load_so2_chunk(so2, c + 1, a.hd);
-                    float x[8];
-                    next_o(c, x);
-                    const float cs8[8] = {sc_cur.a.x, sc_cur.a.y, sc_cur.a.z, sc_cur.a.w, sc_cur.b.x, sc_cur.b.y, sc_cur.b.z, sc_cur.b.w};
-                    so2_apply<true>(x, cs8);
-                    emit(c, x);
-                    sc_cur = sc_nxt;
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&bars[L::bOFree + X]);                  // O_X fully read: the next item's PV_X(0) may overwrite it
-            if (a.lse && valid)
-                a.lse[(static_cast<int64_t>(ic.b) * a.H + ic.h) * a.Tq + t] = m_used * a.scale + logf(l_run);
-            if (dbg) {
-                const long long d_t3 = clock64();
-                d_loop += d_t1 - d_t0; d_wait_o += d_t2 - d_t1; d_epi += d_t3 - d_t2; ++d_items;
-                d_e[0] += e0 - d_t2; d_e[1] += e1 - e0; d_e[2] += e2 - e1; d_e[3] += d_t3 - e2;
-            }
-        }
-        if (dbg) {
-            dbg[0] = clock64() - d_start; dbg[1] = d_loop; dbg[2] = d_epi; dbg[3] = d_wait_s; dbg[4] = d_wait_o;
-            dbg[5] = d_items; dbg[6] = d_e[0]; dbg[7] = d_e[1]; dbg[13] = d_e[2]; dbg[14] = d_e[3];
-        }
-    } else if (warp >= 12) {
-        // =========================================================== staging warps: K'/V' units + Q' of the next item
-        setmaxnreg_dec<GTA_REG_STAGE>();
-        const int st = threadIdx.x - 384;    // 0..127; row `st` of every Q tile
-        uint32_t cntx[2] = {0, 0};           // items staged per tile slot (buffer = cnt & 1, phase = (cnt >> 1) & 1)
-        const int G_ = gridDim.x;
-        const int nrounds = (nitems + G_ - 1) / G_;
-        int ucur = blockIdx.x;               // next unit of this CTA
-        if (f.flags) {
-#pragma unroll 1
-            for (int i = 0; i < kPfUnits; ++i) {
-                const int u2 = ucur + i * gridDim.x;
-                if (u2 < f.nunits) {
-                    const int bh2 = u2 / n;
-                    prefetch_kv_unit<TIn, D>(f.rot, u2 - bh2 * n, bh2 % a.H, bh2 / a.H, st);
-                }
-            }
-        }
-        // staging clocks (kDbg): second plane of the debug buffer, [gridDim.x + cta][16]
-        long long* sdbg = (kDbg && a.dbg && st == 0) ? a.dbg + (static_cast<size_t>(gridDim.x) + blockIdx.x) * 16 : nullptr;
-        long long s_unit = 0, s_q = 0, s_qwait = 0, s_units = 0, s_bar = 0;
-        const long long s_start = sdbg ? clock64() : 0;
-#pragma unroll 1
-        for (int rnd = 0; rnd < nrounds; ++rnd) {
-            if (f.flags) {
-                // every unit of the (b,h)s that round `rnd` touches, in the order the items need them
-                const long long last = (static_cast<long long>(rnd + 1) * G_ < nitems ? static_cast<long long>(rnd + 1) * G_ : nitems) - 1;
-                const int uneed = (static_cast<int>(last / npairs) + 1) * n;
-#pragma unroll 1
-                while (ucur < uneed) {
-                    const int bh = ucur / n;
-                    if (ucur + kPfUnits * G_ < f.nunits) {   // a later unit of this CTA: raw rows into L2 while this one is rotated
-                        const int u2 = ucur + kPfUnits * G_, bh2 = u2 / n;
-                        prefetch_kv_unit<TIn, D>(f.rot, u2 - bh2 * n, bh2 % a.H, bh2 / a.H, st);
-                    }
-                    const long long u0 = sdbg ? clock64() : 0;
-                    stage_kv_unit<TIn, D>(f.rot, ucur - bh * n, bh % a.H, bh / a.H, st, tc);
-                    fence_proxy_async_global();          // the tile images are read through the async proxy (bulk copies)
-                    const long long u1 = sdbg ? clock64() : 0;
-                    named_bar_sync(1, kStagerThreads4);
-                    if (sdbg) { const long long u2 = clock64(); s_unit += u1 - u0; s_bar += u2 - u1; ++s_units; }
-                    if (st == 0) {
-                        __threadfence();
-                        st_release_gpu(f.flags + ucur, 1);
-                    }
-                    ucur += G_;
-                }
-            }
-            if (kQWarps != 0) continue;                  // Q' is staged by warps 10-11
-            const int item = blockIdx.x + rnd * G_;
-            if (item >= nitems) continue;
-            const ItemCoord4 ic = decode_item4(item, npairs, a.H, a.Tq);
-            if (item + G_ < nitems) {                    // raw Q rows of the next round's item into L2
-                const ItemCoord4 nx_ = decode_item4(item + G_, npairs, a.H, a.Tq);
-                prefetch_q_row(nx_, 0, st);
-                prefetch_q_row(nx_, 1, st);
-            }
-#pragma unroll 1
-            for (int X = 0; X < 2; ++X) {
-                if (X == 1 && !ic.has_b) continue;
-                const uint32_t c_ = cntx[X]++;
-                const int buf = c_ & 1;
-                const long long q0 = sdbg ? clock64() : 0;
-                if (c_ >= 2) mbar_wait(&bars[L::bQFree + buf * 2 + X], ((c_ >> 1) - 1) & 1);
-                const long long q1 = sdbg ? clock64() : 0;
-                stage_q_row(ic, X, smem + L::kQ + (buf * 2 + X) * L::kTile, st);
-                fence_proxy_async_smem();
-                mbar_arrive(&bars[L::bQFull + buf * 2 + X]);
-                if (sdbg) { s_qwait += q1 - q0; s_q += clock64() - q1; }
-            }
-        }
-        if (sdbg) {
-            sdbg[0] = clock64() - s_start; sdbg[1] = s_unit; sdbg[2] = s_bar; sdbg[3] = s_units; sdbg[4] = s_q; sdbg[5] = s_qwait;
-        }
-    } else {
-      setmaxnreg_dec<GTA_REG_ISSUE>();
-      if (warp == 8) {
-            // ======================================================= UMMA issuer
-            constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, 0, 1);
-            uint32_t gk = 0;                   // global key-tile counter of this CTA (K/V ring position)
-            uint32_t gtx[2] = {0, 0};          // tiles per softmax warpgroup (p_full phase)
-            uint32_t cntx[2] = {0, 0};         // items per tile slot (Q buffer / o_free phase)
-            const uint32_t bar0 = smem_u32(bars);
-            long long* dbg = (kDbg && a.dbg && lane == 0) ? a.dbg + static_cast<size_t>(blockIdx.x) * 16 : nullptr;
-            long long w_k = 0, w_v = 0, w_p = 0, w_of = 0, w_q = 0;
-#define GTA_TIMED_WAIT(acc, ...)                                 \
-    do {                                                         \
-        const long long t0_ = dbg ? clock64() : 0;               \
-        __VA_ARGS__;                                             \
-        if (dbg) acc += clock64() - t0_;                         \
-    } while (0)
-
-#pragma unroll 1
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const ItemCoord4 ic = decode_item4(item, npairs, a.H, a.Tq);
-                const int nx = ic.has_b ? 2 : 1;
-                uint32_t q_addr[2];
-                for (int X = 0; X < nx; ++X) {
-                    const uint32_t c_ = cntx[X];
-                    const int buf = c_ & 1;
-                    q_addr[X] = smem_u32(smem + L::kQ + (buf * 2 + X) * L::kTile);
-                }
-
-                auto issue_qk = [&](int X, int j) {
-                    const int s = (gk + j) % NS;
-                    if (elect_one()) {
-                        const uint64_t qd = desc_kmajor_sw64(q_addr[X], 0);
-                        const uint64_t kd = desc_kmajor_sw64(smem_u32(smem + L::kK + s * L::kTile), 0);
-                        const uint32_t qlo = static_cast<uint32_t>(qd), qhi = static_cast<uint32_t>(qd >> 32);
-                        const uint32_t klo = static_cast<uint32_t>(kd), khi = static_cast<uint32_t>(kd >> 32);
-                        const uint32_t d_addr = tmem_base + (X ? k4TmemSB : k4TmemSA);
-#pragma unroll
-                        for (int kk = 0; kk < D / 16; ++kk)
-                            umma_ss_lohi(d_addr, qlo + kstep_kmajor_sw64(kk), qhi, klo + kstep_kmajor_sw64(kk), khi, idesc_qk, kk > 0);
-                        if (X == nx - 1) umma_commit_addr(bar0 + (L::bKEmpty + s) * 8);
-                        if (j == n - 1) umma_commit_addr(bar0 + (L::bQFree + (cntx[X] & 1) * 2 + X) * 8);
-                        umma_commit_addr(bar0 + (L::bSFull + X) * 8);
-                    }
-                    __syncwarp();
-                };
-                auto issue_pv = [&](int X, int j) {
-                    const int s = (gk + j) % NS;
-                    GTA_TIMED_WAIT(w_p, mbar_wait(&bars[L::bPFull + X], (gtx[X] + j) & 1));
-                    if (j == 0 && cntx[X] > 0) GTA_TIMED_WAIT(w_of, mbar_wait(&bars[L::bOFree + X], (cntx[X] - 1) & 1));
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t vd = desc_mnmajor_sw64(smem_u32(smem + L::kV + s * L::kTile), 0);
-                        const uint32_t vlo = static_cast<uint32_t>(vd), vhi = static_cast<uint32_t>(vd >> 32);
-                        const uint32_t d_addr = tmem_base + (X ? k4TmemOB : k4TmemOA);
-                        const uint32_t p_addr = tmem_base + (X ? k4TmemSB : k4TmemSA);
-#pragma unroll
-                        for (int kk = 0; kk < 8; ++kk)
-                            umma_ts_lohi(d_addr, p_addr + kk * 8, vlo + kstep_mnmajor_sw64(kk), vhi, idesc_pv,
-                                         (j > 0 || kk > 0) ? 1u : 0u);
-                        if (X == nx - 1) umma_commit_addr(bar0 + (L::bVEmpty + s) * 8);
-                        if (j == n - 1) umma_commit_addr(bar0 + (L::bOFinal + X) * 8);
-                    }
-                    __syncwarp();
-                };
-
-                GTA_TIMED_WAIT(w_k, mbar_wait(&bars[L::bKFull + gk % NS], (gk / NS) & 1));
-                for (int X = 0; X < nx; ++X) {
-                    const uint32_t c_ = cntx[X];
-                    GTA_TIMED_WAIT(w_q, mbar_wait(&bars[L::bQFull + (c_ & 1) * 2 + X], (c_ >> 1) & 1));
-                    tc_fence_after();
-                    issue_qk(X, 0);
-                }
-#pragma unroll 1
-                for (int j = 0; j < n; ++j) {
-                    GTA_TIMED_WAIT(w_v, mbar_wait(&bars[L::bVFull + (gk + j) % NS], ((gk + j) / NS) & 1));
-                    if (j + 1 < n) GTA_TIMED_WAIT(w_k, mbar_wait(&bars[L::bKFull + (gk + j + 1) % NS], ((gk + j + 1) / NS) & 1));
-                    for (int X = 0; X < nx; ++X) {
-                        issue_pv(X, j);
-                        if (j + 1 < n) issue_qk(X, j + 1);
-                    }
-                }
-                gk += n;
-                for (int X = 0; X < nx; ++X) { gtx[X] += n; ++cntx[X]; }
-            }
-            if (dbg) { dbg[8] = w_k; dbg[9] = w_v; dbg[10] = w_p; dbg[11] = w_of; dbg[12] = w_q; }
-#undef GTA_TIMED_WAIT
-      } else if (warp >= 10) {
-        if (kQWarps != 0) {
-            // ======================================================= Q stager (warps 10-11; runs one item ahead)
-            const int r0 = threadIdx.x - 320;    // 0..63; rows r0 and r0 + 64 of each tile
-            uint32_t cntx[2] = {0, 0};
-#pragma unroll 1
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const ItemCoord4 ic = decode_item4(item, npairs, a.H, a.Tq);
-                if (item + static_cast<int>(gridDim.x) < nitems) {
-                    const ItemCoord4 nx_ = decode_item4(item + gridDim.x, npairs, a.H, a.Tq);
-                    prefetch_q_row(nx_, 0, r0); prefetch_q_row(nx_, 0, r0 + 64);
-                    prefetch_q_row(nx_, 1, r0); prefetch_q_row(nx_, 1, r0 + 64);
-                }
-#pragma unroll 1
-                for (int X = 0; X < 2; ++X) {
-                    if (X == 1 && !ic.has_b) continue;
-                    const uint32_t c_ = cntx[X]++;
-                    const int buf = c_ & 1;
-                    if (c_ >= 2) mbar_wait(&bars[L::bQFree + buf * 2 + X], ((c_ >> 1) - 1) & 1);
-                    uint8_t* sQ = smem + L::kQ + (buf * 2 + X) * L::kTile;
-#pragma unroll 1
-                    for (int rr = 0; rr < 2; ++rr) stage_q_row(ic, X, sQ, r0 + rr * 64);
-                    fence_proxy_async_smem();
-                    mbar_arrive(&bars[L::bQFull + buf * 2 + X]);
-                }
-            }
-        }
-      } else if (warp == 9) {
-            // ======================================================= bulk-copy producer
-            uint32_t gk = 0;
-#pragma unroll 1
-            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const ItemCoord4 ic = decode_item4(item, npairs, a.H, a.Tq);
-                const size_t blob0 = (static_cast<size_t>(ic.b) * a.H + ic.h) * n;
-                if (f.flags) {
-                    // K'/V' of this (b,h) are rotated by the staging warps of this and other CTAs: wait for their flags
-                    const int* fl = f.flags + blob0;
-#pragma unroll 1
-                    for (int j0 = 0; j0 < n; j0 += 32) {
-                        if (j0 + lane < n) {
-                            while (ld_acquire_gpu(fl + j0 + lane) == 0) __nanosleep(40);
-                        }
-                    }
-                    __syncwarp();
-                    fence_proxy_async_global();
-                }
-#pragma unroll 1
-                for (int j = 0; j < n; ++j, ++gk) {
-                    const int s = gk % NS;
-                    if (gk >= NS) mbar_wait(&bars[L::bKEmpty + s], ((gk / NS) - 1) & 1);
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&bars[L::bKFull + s], L::kTile);
-                        bulk_g2s(smem + L::kK + s * L::kTile, a.ws_k + (blob0 + j) * L::kTile, L::kTile, &bars[L::bKFull + s]);
-                    }
-                    if (gk >= NS) mbar_wait(&bars[L::bVEmpty + s], ((gk / NS) - 1) & 1);
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(&bars[L::bVFull + s], L::kTile);
-                        bulk_g2s(smem + L::kV + s * L::kTile, a.ws_v + (blob0 + j) * L::kTile, L::kTile, &bars[L::bVFull + s]);
-                    }
-                    __syncwarp();
-                }
-            }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 8) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
-    }
-}
-
-template <typename TIn, typename TOut, int D>
-static int launch4_one(const AttnArgs& a, const Fused4Args& f, const GtaAttnParams& p, cudaStream_t st) {
-    using L = Attn4Cfg<D>;
-    auto kern = attn_fwd4_kernel<TIn, TOut, D, false>;
-    if (a.dbg) {
-        // the instrumented build exists for the headline instantiation only
-        if (D == 96 && sizeof(TIn) == 2 && sizeof(TOut) == 2) kern = attn_fwd4_kernel<TIn, TOut, D, (D == 96 && sizeof(TIn) == 2 && sizeof(TOut) == 2)>;
-        else return set_error(GTA_ERR_UNSUPPORTED, "debug_clocks: bf16 in/out, head dim 96 only");
-    }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::kBytes));
-    if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    // The CTAs wait on each other's K'/V' units: the whole grid must be co-resident (one CTA per SM).
-    static thread_local int num_sms = 0, cached_dev = -1;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != cached_dev) {
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-        cached_dev = dev;
-    }
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads4, L::kBytes);
-    if (e != cudaSuccess || per_sm < 1) return set_error(GTA_ERR_CUDA, "fused attention kernel does not fit an SM");
-    const int npairs = (p.Tq + 255) / 256;
-    const long long nitems = static_cast<long long>(p.B) * p.H * npairs;
-    if (nitems > 0x7fffffffLL || static_cast<long long>(f.nunits) + p.Tk > 0x7fffffffLL)
-        return set_error(GTA_ERR_UNSUPPORTED, "too many work items");
-    const int grid = static_cast<int>(nitems < num_sms ? nitems : num_sms);
-    if (f.flags) {
-        e = cudaMemsetAsync(f.flags, 0, static_cast<size_t>(f.nunits) * sizeof(int), st);
-        if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
-    }
-    kern<<<grid, kThreads4, L::kBytes, st>>>(a, f, npairs, static_cast<int>(nitems));
-    return check_launch("gta_attn_fwd");
-}
+int launch_attn_fwd_v3_ct(const GtaAttnParams& p, const AttnArgs& a, const Fused4Args& f, cudaStream_t st, bool* handled);
 
 template <typename TIn, typename TOut>
 static int launch4_d(const AttnArgs& a, const Fused4Args& f, const GtaAttnParams& p, cudaStream_t st) {
     switch (p.D) {
-        case 32: return launch4_one<TIn, TOut, 32>(a, f, p, st);
-        case 64: return launch4_one<TIn, TOut, 64>(a, f, p, st);
-        case 96: return launch4_one<TIn, TOut, 96>(a, f, p, st);
+        case 32: return launch4_one<TIn, TOut, 32, void>(a, f, p, st);
+        case 64: return launch4_one<TIn, TOut, 64, void>(a, f, p, st);
+        case 96: return launch4_one<TIn, TOut, 96, void>(a, f, p, st);
     }
     return set_error(GTA_ERR_UNSUPPORTED, "persistent pipeline supports head dims 32/64/96");
 }
@@ -771,6 +25,11 @@ int launch_attn_fwd_v3(const GtaAttnParams& p, bool fused, cudaStream_t st) {
     f.nunits = p.B * p.H * a.ntiles_k;
     f.flags = fused ? reinterpret_cast<int*>(static_cast<uint8_t*>(p.workspace) + kv_flags_offset(p.B, p.H, p.Tk, p.D)) : nullptr;
     const bool ib = p.in_dtype == GTA_DTYPE_BF16, ob = p.out_dtype == GTA_DTYPE_BF16;
+    if (ib && !p.debug_clocks && !(p.flags & GTA_FLAG_RUNTIME_LAYOUT)) {      // shipped layouts: staging code specialised at compile time
+        bool handled = false;
+        const int rc = launch_attn_fwd_v3_ct(p, a, f, st, &handled);
+        if (handled) return rc;
+    }
     if (ib && ob) return launch4_d<__nv_bfloat16, __nv_bfloat16>(a, f, p, st);
     if (ib && !ob) return launch4_d<__nv_bfloat16, float>(a, f, p, st);
     if (!ib && ob) return launch4_d<float, __nv_bfloat16>(a, f, p, st);

@@ -46,22 +46,6 @@ constexpr float k5RescaleThreshold = 8.0f;   // log2 units
 #endif
 static_assert(2 * GTA5_REG_SOFTMAX + GTA5_REG_ISSUE + GTA5_REG_EPI <= 512, "register split exceeds the register file");
 
-template <int TRIV, int SE3, int SO3, int SO2>
-struct HeadLayout {
-    static constexpr int kTriv = TRIV, kSe3 = SE3, kSo3 = SO3, kSo2 = SO2;
-    static constexpr int D = TRIV + SE3 + SO3 + SO2;
-    static constexpr int c1 = TRIV / 8, c2 = c1 + SE3 / 8, c3 = c2 + SO3 / 8, c4 = c3 + SO2 / 8;   // chunk boundaries
-    static_assert(TRIV % 8 == 0 && SE3 % 8 == 0 && SO3 % 8 == 0 && SO2 % 8 == 0, "blocks are whole 16-byte chunks");
-};
-
-template <int I, int N, typename F>
-__device__ __forceinline__ void static_for(F&& f) {
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
-
 template <int D>
 struct Attn5Cfg {
     static constexpr int kStages = 2;

@@ -7,6 +7,8 @@
 //   so3 chunk = [3 | 5] multiplied by Wigner D_1, D_2 of the view (gta.py:182-201, :259-268)
 //   so2 chunk = four (x,y) pairs, each rotated by the token's angle (gta.py:203-219, :269-271)
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace gta {
@@ -395,6 +397,84 @@ __device__ __forceinline__ void stage_row(const TIn* __restrict__ arow, const TI
             }
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// stage_row with the head layout known at compile time (LY = HeadLayout<triv, se3, so3, so2>): straight-line code, every
+// raw chunk of a batch (the whole row for bf16) requested up front, view matrices loaded once, no per-chunk block-type
+// logic.  kNB = number of batches the row is split into (1 for bf16, more for fp32 inputs to bound the raw registers).
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for_(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for_<I + 1, N>(f);
+    }
+}
+template <typename TIn, typename LY, int kMode, bool kPair, int kNB, typename Store>
+__device__ __forceinline__ void stage_row_ct(const TIn* __restrict__ arow, const TIn* __restrict__ brow, const bool valid,
+                                             const bool rot_b, const float* __restrict__ se3m, const float* __restrict__ so3m,
+                                             const float* __restrict__ so2cs, const float tc, Store&& store) {
+    constexpr bool kT = (kMode == kModeQ || kMode == kModeKVT);
+    constexpr bool kInv = (kMode == kModeOut || kMode == kModeKVT);
+    constexpr int NC = LY::D / 8;
+    static_assert(NC % kNB == 0, "batches must divide the row");
+    constexpr int CB = NC / kNB;
+    float M[LY::kSe3 ? 16 : 1], W[LY::kSo3 ? 34 : 1];
+    static_for_<0, kNB>([&](auto ib) {
+        constexpr int c0 = decltype(ib)::value * CB;
+        RawChunk<TIn> ra[CB], rb[kPair ? CB : 1];
+#pragma unroll
+        for (int i = 0; i < CB; ++i) {
+            zero_raw(ra[i]);
+            if (kPair) zero_raw(rb[i]);
+            if (valid) {
+                load_raw(arow + (c0 + i) * 8, ra[i]);
+                if (kPair) load_raw(brow + (c0 + i) * 8, rb[i]);
+            }
+        }
+        static_for_<0, CB>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int c = c0 + i;
+            float xa[8], xb[8];
+            raw_to_f32(ra[i], xa);
+            if (kPair) raw_to_f32(rb[i], xb);
+            if constexpr (c >= LY::c1 && c < LY::c2) {
+                if constexpr (c == LY::c1) {                     // first se3 chunk of the row: the view matrix, once
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(se3m) + q);
+                        M[4 * q] = r4.x; M[4 * q + 1] = r4.y; M[4 * q + 2] = r4.z; M[4 * q + 3] = r4.w;
+                    }
+                }
+                if (valid) {
+                    if (kT) se3_apply_T(xa, M, tc); else se3_apply(xa, M, tc);
+                    if (kPair && rot_b) { if (kT) se3_apply_T(xb, M, tc); else se3_apply(xb, M, tc); }
+                }
+            } else if constexpr (c >= LY::c2 && c < LY::c3) {
+                if constexpr (c == LY::c2) {
+#pragma unroll
+                    for (int q = 0; q < 17; ++q) {
+                        const float2 r2 = __ldg(reinterpret_cast<const float2*>(so3m) + q);
+                        W[2 * q] = r2.x; W[2 * q + 1] = r2.y;
+                    }
+                }
+                if (valid) {
+                    so3_apply<kInv>(xa, W);
+                    if (kPair && rot_b) so3_apply<kInv>(xb, W);
+                }
+            } else if constexpr (c >= LY::c3) {
+                const float4* p4 = reinterpret_cast<const float4*>(so2cs + (c - LY::c3) * 8);
+                const float4 ca = __ldg(p4), cb = __ldg(p4 + 1);
+                const float c8[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                if (valid) {
+                    so2_apply<kInv>(xa, c8);
+                    if (kPair && rot_b) so2_apply<kInv>(xb, c8);
+                }
+            }
+            store(c, xa, xb);
+        });
+    });
 }
 
 }  // namespace gta

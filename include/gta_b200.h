@@ -112,6 +112,8 @@ typedef struct GtaAttnParams {
                                     head layouts without an instantiation fall back to the gta_attn_fwd3.cu kernel */
 #define GTA_FLAG_V5_PIPELINE 512 /* two launches; attention kernel with the spare P buffer in tensor memory (gta_attn_fwd6.cu): QK_X(j+1) is
                                     issued while the exponentials of tile j still run, on every other key tile */
+#define GTA_FLAG_RUNTIME_LAYOUT 2048 /* single-launch kernel: use the run-time-layout staging code even for a layout that has a
+                                       compile-time-specialised instantiation (A/B measurement, tests) */
 #define GTA_FLAG_V3_PRESTAGED 64 /* with GTA_FLAG_SKIP_STAGE: run the single-launch kernel on an already staged workspace
                                    (its rotation warps idle) instead of the two-launch attention kernel */
 
