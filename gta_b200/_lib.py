@@ -21,6 +21,7 @@ GTA_FLAG_V1_PIPELINE = 16
 GTA_FLAG_SINGLE_LAUNCH = 32
 GTA_FLAG_TWO_LAUNCH = 1024
 GTA_FLAG_RUNTIME_LAYOUT = 2048
+GTA_FLAG_BWD_SPLIT = 4096
 GTA_PIPELINE_NAMES = {0: "two launches", 1: "single launch", 2: "split precision", 3: "generic"}
 GTA_FLAG_V3_PRESTAGED = 64
 GTA_FLAG_V4_PIPELINE = 256

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgta_b200.so")
-SOURCES = ["gta_abi.cu", "gta_reps.cu", "gta_rotate_kv.cu", "gta_generic.cu", "gta_attn_fwd2.cu", "gta_attn_fwd3.cu", "gta_attn_fwd4.cu", "gta_attn_fwd4_ct.cu", "gta_attn_fwd5a.cu", "gta_attn_fwd5b.cu", "gta_attn_fwd6.cu", "gta_attn_fwd_hp.cu", "gta_attn_bwd.cu"]
+SOURCES = ["gta_abi.cu", "gta_reps.cu", "gta_rotate_kv.cu", "gta_generic.cu", "gta_attn_fwd2.cu", "gta_attn_fwd3.cu", "gta_attn_fwd4.cu", "gta_attn_fwd4_ct.cu", "gta_attn_fwd5a.cu", "gta_attn_fwd5b.cu", "gta_attn_fwd6.cu", "gta_attn_fwd_hp.cu", "gta_attn_bwd.cu", "gta_attn_bwd2.cu"]
 # development library (probes, micro-benchmarks, the first-generation kernel): include/gta_b200_dev.h
 DEV_SOURCES = ["gta_dev_abi.cu", "gta_attn_fwd.cu"]
 DEV_OUT = os.path.join(HERE, "libgta_b200_dev.so")

@@ -22,27 +22,10 @@
 // (register pressure in the epilogue), so kNW = 2.
 #include <cmath>
 
-#include "attn_common.cuh"
+#include "gta_attn_bwd.cuh"
 
 namespace gta {
 
-struct BwdArgs {
-    const uint8_t* q_img; const uint8_t* do_img;     // [B*H*ntq] tile images of Q', dO'
-    const uint8_t* k_img; const uint8_t* v_img;      // [B*H*ntk] tile images of K', V'
-    const float* lse; const float* delta;            // [B,H,Tq]
-    void* dq; void* dk; void* dv;                    // [B,T,H,D] contiguous
-    const void* q; const void* k; const void* v;     // raw inputs (trans_coeff terms)
-    int64_t q_sb, q_sh, q_st, k_sb, k_sh, k_st, v_sb, v_sh, v_st;
-    float* dtc;
-    int B, H, Tq, Tk, Nq, Nk, tpvq, tpvk, ntq, ntk, C;
-    HeadDims hd;
-    const float* se3_q; const float* so3_q; const float* so2_q;
-    const float* se3_k; const float* so3_k; const float* so2_k;
-    const float* tc_ptr;
-    float scale, scale_log2;
-    int v_transform;
-    long long* dbg;      // optional [2 kernels][num CTAs][16] clock64 phase sums (tools/bwd_phase_timing.py)
-};
 
 #ifndef GTA_BWD_NW
 #define GTA_BWD_NW 2
@@ -72,15 +55,9 @@ struct BwdSmem {
     static constexpr uint32_t kBytes = (kUsed + 1024 > 120u * 1024u) ? kUsed + 1024 : 120u * 1024u;
 };
 
-__device__ __forceinline__ void bwd_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 // TMEM column of the packed bf16 A operand for K-step kk (16 rows of the streamed tile): the first compute warpgroup packs
 // columns 0..63 into 0..31, the second 64..127 into 64..95.
 __device__ __forceinline__ constexpr uint32_t pk_off(int kk) { return (kk / (kCW / 16)) * kCW + (kk % (kCW / 16)) * 8u; }
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // Shared skeleton of the two kernels.  kDKV = true : fixed tiles K'_j, V'_j; streamed Q'_i, dO'_i; rows = keys.
 //                                      kDKV = false: fixed tiles Q'_i, dO'_i; streamed K'_j, V'_j; rows = queries.
@@ -535,7 +512,7 @@ size_t attn_bwd_workspace_bytes(int B, int H, int Tq, int Tk, int D) {
     const size_t tile = kv_tile_bytes(D);
     const size_t ntq = num_kv_tiles(Tq), ntk = num_kv_tiles(Tk);
     return 2 * bwd_align(static_cast<size_t>(B) * H * ntq * tile) + bwd_align(2 * static_cast<size_t>(B) * H * ntk * tile) +
-           bwd_align(static_cast<size_t>(B) * H * Tq * 4);
+           bwd_align(static_cast<size_t>(B) * H * Tq * 4) + (bwd_fused_supported(D) ? bwd_align(bwd_dq_acc_bytes(B, H, Tq, D)) : 0);
 }
 
 template <typename TIn, typename TOut, int D>
@@ -622,6 +599,10 @@ int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st) {
     a.scale = p.scale; a.scale_log2 = p.scale * 1.4426950408889634f;
     a.v_transform = p.v_transform;
     a.dbg = p.debug_clocks;
+    a.dq_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(delta) + bwd_align(static_cast<size_t>(p.B) * p.H * p.Tq * 4));
+    // head dims <= 96: ONE kernel for dK, dV and the dQ' partial sums (gta_attn_bwd2.cu); GTA_FLAG_BWD_SPLIT keeps the
+    // dK/dV + dQ kernel pair (the only path for head dim 128)
+    if (bwd_fused_supported(p.D) && !(p.flags & GTA_FLAG_BWD_SPLIT)) return launch_bwd_fused(a, bf, p.D, (p.flags & GTA_FLAG_RUNTIME_LAYOUT) != 0, st);
     return bf ? launch_bwd_t<__nv_bfloat16>(a, p.D, st) : launch_bwd_t<float>(a, p.D, st);
 }
 

@@ -43,10 +43,11 @@ def main():
         return e0.elapsed_time(e1) / n
 
     ms_f = timed(lambda: ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True))
-    ms_b = timed(lambda: ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc))
+    flags = int(os.environ.get("GTA_BWD_FLAGS", "0"))      # 4096 = GTA_FLAG_BWD_SPLIT (dK/dV kernel + dQ kernel)
+    ms_b = timed(lambda: ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=flags))
     H, D, Tq, Tk = cfg.heads, cfg.head_dim, nq * tq, nk * tk
     f_fwd = 4.0 * B * H * Tq * Tk * D
-    print(json.dumps({"workload": name, "batch": B, "fwd_ms": ms_f, "bwd_ms": ms_b,
+    print(json.dumps({"workload": name, "batch": B, "bwd_flags": flags, "fwd_ms": ms_f, "bwd_ms": ms_b,
                       "fwd_tflops": f_fwd / ms_f / 1e9, "bwd_tflops_algorithmic(2.5x fwd flops)": 2.5 * f_fwd / ms_b / 1e9,
                       "bwd_tflops_executed(3.5x: S and dP recomputed in both kernels)": 3.5 * f_fwd / ms_b / 1e9,
                       "fwd_bwd_Mtok_s": B * Tq / (ms_f + ms_b) / 1e3}))

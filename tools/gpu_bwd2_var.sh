@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+GTA_B200_LIB=$PWD/gta_b200/libgta_b200_dbg.so timeout 250 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -s -k "fused_kernel_matches_kernel_pair" > gpurun_out/bwd2_dbg.log 2>&1
+grep -E "passed|failed|error" gpurun_out/bwd2_dbg.log | tail -3
+grep "timed out" gpurun_out/bwd2_dbg.log | awk '{print "block",$7,"warp",int($9/32),"bar",$10,"parity",$12}' | sort | uniq -c | sort -k3n -k5n | head -40
+if grep -q "failed\|error\|timed out" gpurun_out/bwd2_dbg.log; then grep -E "Error|assert" gpurun_out/bwd2_dbg.log | head; exit 1; fi
+timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "backward" 2>&1 | tail -2
+for v in ${VARIANTS:-""}; do
+  [ "$v" = "main" ] && v=""
+  echo "== variant libgta_b200$v.so"
+  for w in ${WL:-"msn_enc:64 clevr_dec:32"}; do
+    GTA_B200_LIB=$PWD/gta_b200/libgta_b200$v.so timeout 200 python tools/bwd_bench.py ${w%%:*} ${w##*:} | cut -c1-110
+    GTA_B200_LIB=$PWD/gta_b200/libgta_b200$v.so timeout 200 python tools/bwd2_phase.py ${w%%:*} ${w##*:}
+  done
+done
