@@ -412,6 +412,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="batch chunks of the host-buffer pipeline (e2e leg)")
     ap.add_argument("--no-backward", action="store_true", help="skip the fused-backward leg (`backward` object)")
+    ap.add_argument("--bwd-flags", type=int, default=0, help="GTA_FLAG_* bits for the backward leg (4096 = the dK/dV + dQ kernel pair)")
     ap.add_argument("--backward", action="store_true", help="(kept for compatibility; the backward leg is on by default)")
     ap.add_argument("--no-info", action="store_true", help="skip the informational GPU legs (reference eager / SDPA on the B200)")
     args = ap.parse_args()
@@ -569,13 +570,16 @@ def main():
     if not args.no_backward:
         out_f, lse_f = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True)
         dout = torch.randn(out_f.shape, device=dev).to(out_f.dtype)
-        bwd_fn = lambda: ops.gta_attention_bwd(dout, q, k, v, out_f, lse_f, reps, cfg.f_dims, trans_coeff=tc)
+        bwd_fn = lambda: ops.gta_attention_bwd(dout, q, k, v, out_f, lse_f, reps, cfg.f_dims, trans_coeff=tc, flags=args.bwd_flags)
         for _ in range(3):
             bwd_fn()
         ms_bwd = timed(bwd_fn, max(3, args.steps // 2))
         bwd_flops = 2.5 * 4.0 * B * H * nq * tq * nk * tk * D
         pk_b, _ = peaks()
-        bwd = {"ms": ms_bwd, "kernels": "K'/V'/Q'/dO' staging + delta + attn_bwd_kernel<dKV> + attn_bwd_kernel<dQ>",
+        fused_bwd = D <= 96 and not (args.bwd_flags & _lib.GTA_FLAG_BWD_SPLIT)
+        bwd = {"ms": ms_bwd,
+               "kernels": ("K'/V'/Q'/dO' staging + delta + attn_bwd_fused_kernel (dK, dV, bulk-reduced dQ partial sums) + bwd_dq_finish_kernel"
+                           if fused_bwd else "K'/V'/Q'/dO' staging + delta + attn_bwd_kernel<dKV> + attn_bwd_kernel<dQ>"),
                "tflops_algorithmic": bwd_flops / (ms_bwd * 1e-3) / 1e12,
                "frac_of_peak": bwd_flops / (ms_bwd * 1e-3) / 1e12 / pk_b["bf16_tflops"],
                "fwd_bwd_Mtokens_per_s": world * B * nq * tq / ((ms_step + ms_bwd) * 1e-3) / 1e6}

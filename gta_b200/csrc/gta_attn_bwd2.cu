@@ -34,16 +34,19 @@ constexpr uint32_t kSmemOptinMax = 232448u;   // 227 KB
 
 template <int D>
 struct FusedSmem {
-    static constexpr int kStages = 3;
+    static constexpr int kStagesQ = 3, kStagesO = 2;
     static constexpr uint32_t kTile = 128u * D * 2u;
     static constexpr uint32_t kFix0 = 0, kFix1 = kTile;          // K'_j, V'_j
-    static constexpr uint32_t kStg0 = 2 * kTile;                  // [3 stages] Q'_i
-    static constexpr uint32_t kStg1 = 5 * kTile;                  // [3 stages] dO'_i
+    // Q'_i is read by S^T(i) — issued a whole pair early — and last by dK'(i): three stages; dO'_i by dP^T(i) and last by
+    // dV'(i), which completes early in its pair: two stages are enough
+    static constexpr uint32_t kStgQ = 2 * kTile;                  // [3 stages] Q'_i
+    static constexpr uint32_t kStgO = 5 * kTile;                  // [2 stages] dO'_i
+    static constexpr uint32_t kDQ = 7 * kTile;                    // fp32 staging of HALF a dQ' partial [D/8][128 rows][16 B] (= kTile bytes)
     static constexpr uint32_t kDS = 8 * kTile;                    // dS^T [2 blocks of 64 queries][128 keys][128 B], 128-byte swizzle
     static constexpr uint32_t kLD = kDS + 32768u;                 // float [2 warpgroups][2 buffers][-lse*log2e 64 | -delta*scale 64]
     static constexpr uint32_t kBars = kLD + 2048u;
-    enum : int { bFix = 0, bFull = 1, bEmpty = 4, bSFull = 7, bDPFull = 8, bPReady = 9, bPdFree = 10, bDQFull = 11, bDQFree = 12,
-                 bDone = 13, bSFree = 14, bCount = 15 };
+    enum : int { bFix = 0, bFullQ = 1, bEmptyQ = 4, bFullO = 7, bEmptyO = 9, bSFull = 11, bDPFull = 12, bPReady = 13, bPdFree = 14,
+                 bDQFull = 15, bDQFree = 16, bDone = 17, bSFree = 18, bPFree = 19, bCount = 20 };
     static constexpr uint32_t kTmemSlot = kBars + bCount * 8;
     static constexpr uint32_t kUsed = kTmemSlot + 16;
     // the dynamic shared-memory window is 1024-byte aligned in practice; the kernel checks (and traps) if the slack is not enough
@@ -52,13 +55,16 @@ struct FusedSmem {
     static_assert(kDS % 1024u == 0, "128-byte-swizzled tile needs 1024-byte alignment");
 };
 
-// p[0..3] += v (fp32), no return value, performed in L2 (SASS: REDG.E.ADD.F32x4): 32 lanes on consecutive 16-byte pieces
-// add four full 128-byte lines per instruction.
-__device__ __forceinline__ void red_add_v4(float* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
-                 "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+// dst[i] += src[i] for `bytes` contiguous bytes of fp32, shared -> global, performed by the L2 (SASS: UBLKRED).  Measured against
+// vector reductions from registers (red.global.add.v4.f32, 24 per thread and pair): those cost the pair loop +1.3 k clk.
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)),
+                 "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // dS^T tile read MN-major (A operand of dQ' = dS K'): M = queries, contiguous in 64-element (128 B) swizzle atoms that are
 // 16 KB apart (LBO); the 8-key groups along K are 1024 B apart (SBO); K-step kk = 16 keys = 2048 B.
@@ -94,7 +100,8 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[L::bFix], 1);
-        for (int s = 0; s < L::kStages; ++s) { mbar_init(&bars[L::bFull + s], 1); mbar_init(&bars[L::bEmpty + s], 1); }
+        for (int s = 0; s < L::kStagesQ; ++s) { mbar_init(&bars[L::bFullQ + s], 1); mbar_init(&bars[L::bEmptyQ + s], 1); }
+        for (int s = 0; s < L::kStagesO; ++s) { mbar_init(&bars[L::bFullO + s], 1); mbar_init(&bars[L::bEmptyO + s], 1); }
         mbar_init(&bars[L::bSFull], 1);
         mbar_init(&bars[L::bDPFull], 1);
         mbar_init(&bars[L::bPReady], 256);
@@ -103,6 +110,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
         mbar_init(&bars[L::bDQFree], 128);
         mbar_init(&bars[L::bDone], 1);
         mbar_init(&bars[L::bSFree], 256);
+        mbar_init(&bars[L::bPFree], 1);
         fence_mbar_init();
     }
     if (warp == 12) {
@@ -147,6 +155,22 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
             if (n + 1 < N) nx_stat = col_stat(qtile(n + 1));  // in flight during this tile
             const float* ld = sLDw + (n & 1) * 128;
             const int ncol = a.Tq - qi * 128 - wgc * 64;      // valid query columns of this warpgroup's half
+            if (n == (N > 1 ? N - 2 : 0)) {
+                // the epilogue's global operands (this key row's raw K or V SE(3) block for the trans_coeff term, its angles)
+                // were last touched by the staging kernels: pull them into L2 now, a DRAM round trip costs the epilogue 3-5 k clk
+                const int tt_ = min(tile * 128 + r, a.Tk - 1);
+                if (a.hd.so2) {
+                    const float* p_ = a.so2_k + (static_cast<size_t>(b) * a.Tk + tt_) * a.C * 2;
+                    prefetch_l2(p_);
+                    prefetch_l2(p_ + a.C * 2 - 1);
+                }
+                if (a.dtc && a.hd.se3) {
+                    const TIn* raw_ = (wgc == 0 ? reinterpret_cast<const TIn*>(a.v) + b * a.v_sb + h * a.v_sh + static_cast<int64_t>(tt_) * a.v_st
+                                                : reinterpret_cast<const TIn*>(a.k) + b * a.k_sb + h * a.k_sh + static_cast<int64_t>(tt_) * a.k_st) + a.hd.triv;
+                    prefetch_l2(raw_);
+                    prefetch_l2(raw_ + a.hd.se3 - 1);
+                }
+            }
             const long long d0 = dbg ? clock64() : 0;
             mbar_wait(&bars[L::bSFull], n & 1);
             tc_fence_after();
@@ -183,8 +207,8 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
                 }
             }
             const long long d2 = dbg ? clock64() : 0;
-            // the previous pair's dV' / dK' / dQ' MMAs must be done reading P^T (tensor memory) and dS^T (shared memory)
-            if (n > 0) mbar_wait(&bars[L::bPdFree], (n - 1) & 1);
+            // the previous pair's dV' MMAs must be done reading P^T (tensor memory)
+            if (n > 0) mbar_wait(&bars[L::bPFree], (n - 1) & 1);
             tmem_st32(lane_base + kFTmemP + wgc * 32, pk);
             const long long d3 = dbg ? clock64() : 0;
             mbar_wait(&bars[L::bDPFull], n & 1);
@@ -217,6 +241,8 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
                     if (2 * u + 1 >= ncol) dr[u] &= (2 * u < ncol) ? 0x0000FFFFu : 0u;
                 }
             }
+            // ... and its dQ' / dK' MMAs reading dS^T (shared memory): they finish last, and this wait comes last
+            if (n > 0) mbar_wait(&bars[L::bPdFree], (n - 1) & 1);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {                     // chunks of 8 queries (K elements of dK', M elements of dQ')
                 const uint32_t off = tile_sw128_offset(r, wgc * 8 + u);
@@ -255,21 +281,21 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
         TOut* gbase = reinterpret_cast<TOut*>(which == 0 ? a.dv : a.dk) + (static_cast<int64_t>(b) * T * a.H + h) * D;
         const float* so2_b = a.so2_k + static_cast<size_t>(b) * T * a.C * 2;
         constexpr uint32_t kEPitch = 2064;
-        uint8_t* stage = smem + L::kStg0 + which * (D / 4) * kEPitch;
-        static_assert(2u * (D / 4) * kEPitch <= 6u * L::kTile + 32768u, "epilogue staging must fit in the streamed-tile + dS buffers");
+        uint8_t* stage = smem + L::kStgQ + which * (D / 4) * kEPitch;
+        static_assert(2u * (D / 4) * kEPitch <= 5u * L::kTile, "epilogue staging must fit in the streamed-tile rings (the dQ' staging tile behind them may still be read)");
         // the view matrices of the warp's first row, requested before the wait for the last MMAs; rows of another view reload them
         int cached_view = min(t0 + w4 * 32, T - 1) / a.tpvk;
         ViewReps vr;
         if (rotate) load_view_reps(vr, a.hd, a.se3_k + (static_cast<size_t>(b) * a.Nk + cached_view) * 16,
                                    a.so3_k + (static_cast<size_t>(b) * a.Nk + cached_view) * 34);
         float dtc_part = 0.f;
-        long long d_done = 0, d_drain = 0;
+        long long d_done = 0, d_drain = 0, d_pre = 0;
         if constexpr (!std::is_void<LY>::value) {
             // ---- head layout known at compile time: the same walk as straight-line code with constant block boundaries
             // (the run-time-layout loop below executes ~8x the instructions per item: index arithmetic with divisions, a 3-way
             // block-type branch, operand rings — with two warps per scheduler that is 20 k clk per CTA)
             constexpr int k1 = LY::c1, k2 = LY::c2, k3 = LY::c3, K = D / 8;
-            constexpr int nSe3 = k2 - k1, nSo2 = K - k3;
+            constexpr int nSo2 = K - k3;
             static_assert(LY::D == D, "layout / head dim mismatch");
             // row / chunk of the lane's item k (constant divisors)
             auto item_rc = [&](auto Kc, int& row, int& ch) {
@@ -282,15 +308,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
                 ch = st + idx - rr * n_t;
                 row = w4 * 32 + rr;
             };
-            RawChunk<TIn> pre_rw[nSe3 > 0 ? nSe3 : 1];
             So2Chunk pre_sc[nSo2 > 0 ? nSo2 : 1];
-            static_for<0, nSe3>([&](auto U) {
-                constexpr int u = decltype(U)::value;
-                zero_raw(pre_rw[u]);
-                int row, ch;
-                item_rc(std::integral_constant<int, k1 + u>{}, row, ch);
-                if (want_tc && t0 + row < T) load_raw(rawbase + (t0 + row) * raw_st + ch * 8, pre_rw[u]);
-            });
             static_for<0, nSo2>([&](auto U) {
                 constexpr int u = decltype(U)::value;
                 pre_sc[u].a = make_float4(1.f, 0.f, 1.f, 0.f); pre_sc[u].b = pre_sc[u].a;
@@ -298,6 +316,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
                 item_rc(std::integral_constant<int, k3 + u>{}, row, ch);
                 if (rotate && t0 + row < T) pre_sc[u] = load_so2_chunk(so2_b + static_cast<size_t>(t0 + row) * a.C * 2, ch, a.hd);
             });
+            d_pre = dbg ? clock64() : 0;
             mbar_wait(&bars[L::bDone], 0);
             tc_fence_after();
             d_done = dbg ? clock64() : 0;
@@ -324,6 +343,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
                                    a.so3_k + (static_cast<size_t>(b) * a.Nk + vw) * 34);
                 }
                 const int t_lo = vw * a.tpvk, t_hi = min(t_lo + a.tpvk, T);
+                const float inv_m33 = want_tc ? 1.0f / vr.M[15] : 0.f;
                 static_for<0, K>([&](auto Kc) {
                     constexpr int k = decltype(Kc)::value;
                     constexpr int sg = k < k1 ? 0 : (k < k2 ? 1 : (k < k3 ? 2 : 3));
@@ -336,14 +356,13 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
                     float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
                     if constexpr (sg == 1) {
                         if (want_tc) {
-                            // d(trans_coeff): the un-rotated gradient times d(rep)/d(tc) applied to the raw input 4-vectors (rows 0..2, column 3)
-                            float xin[8];
-                            raw_to_f32(pre_rw[k - k1], xin);
-                            float part = 0.f;
-#pragma unroll
-                            for (int v4 = 0; v4 < 2; ++v4)
-                                part += (x[4 * v4] * vr.M[3] + x[4 * v4 + 1] * vr.M[7] + x[4 * v4 + 2] * vr.M[11]) * xin[4 * v4 + 3];
-                            if (mine) dtc_part += part;
+                            // d(trans_coeff): the un-rotated gradient times d(rep)/d(tc) applied to the raw input 4-vectors (rows 0..2,
+                            // column 3).  The raw w components come from the K' / V' tile image that sits in shared memory anyway
+                            // (w' = M33 w: no global load of the raw rows, whose 32-line accesses stalled the load/store unit)
+                            const uint4 kv = *reinterpret_cast<const uint4*>(smem + (which == 0 ? L::kFix1 : L::kFix0) + tile_sw64_offset(row, ch));
+                            const float part = (x[0] * vr.M[3] + x[1] * vr.M[7] + x[2] * vr.M[11]) * bf16_hi(kv.y) +
+                                               (x[4] * vr.M[3] + x[5] * vr.M[7] + x[6] * vr.M[11]) * bf16_hi(kv.w);
+                            if (mine) dtc_part += part * inv_m33;
                         }
                         if (rotate) se3_apply_T(x, vr.M, tc);
                     } else if constexpr (sg == 2) {
@@ -478,36 +497,49 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
         if (dbg) {
             const long long d_end = clock64();
             dbg[0] = d_end - d_start; dbg[1] = d_ws; dbg[2] = d_exp; dbg[3] = d_wpd; dbg[4] = d_wdp; dbg[5] = d_ds; dbg[6] = N;
-            dbg[7] = d_tail; dbg[8] = d_loop_end - d_start; dbg[9] = d_done - d_loop_end; dbg[10] = d_drain - d_done; dbg[11] = d_end - d_drain; dbg[12] = d_lds;
+            dbg[7] = d_tail; dbg[8] = d_loop_end - d_start; dbg[9] = d_done - d_loop_end; dbg[10] = d_drain - d_done; dbg[11] = d_end - d_drain; dbg[12] = d_lds; dbg[13] = d_pre ? d_pre - d_loop_end : 0;
         }
     } else if (warp < 12) {
         // =========================================================== reducer warpgroup: thread r <-> query row r of the dQ' partial
+        // The partial leaves in two halves of D/2 columns through ONE half-size staging tile: tensor memory -> registers -> shared
+        // memory -> bulk reduction into the fp32 accumulation tile.  dQ' is released when its second half is in registers.
         setmaxnreg_dec<88>();
         const int r = threadIdx.x - 256;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-        float* acc_bh = a.dq_acc + bh * a.ntq * (128u * D) + r * 4;
+        uint8_t* stage = smem + L::kDQ;
+        float* acc_bh = a.dq_acc + bh * a.ntq * (128u * D);
+        constexpr int kHalf = D / 2;
 #pragma unroll 1
         for (int n = 0; n < N; ++n) {
             float* dst = acc_bh + static_cast<size_t>(qtile(n)) * (128u * D);
             mbar_wait(&bars[L::bDQFull], n & 1);
             tc_fence_after();
 #pragma unroll
-            for (int t3 = 0; t3 < D / 32; ++t3) {
-                uint32_t v[32];
-                tmem_ld32(lane_base + kFTmemDP + t3 * 32, v);
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t v[kHalf];
+                if constexpr (kHalf >= 32) tmem_ld32(lane_base + kFTmemDP + hf * kHalf, v);
+                if constexpr (kHalf % 32 == 16) tmem_ld16(lane_base + kFTmemDP + hf * kHalf + (kHalf / 32) * 32, v + (kHalf / 32) * 32);
                 tmem_ld_wait();
-                if (t3 == D / 32 - 1) {                       // dQ' is in registers: dP^T of the next pair may overwrite it
+                if (hf == 1) {                                // dQ' is in registers: dP^T of the next pair may overwrite it
                     tc_fence_before();
                     mbar_arrive(&bars[L::bDQFree]);
                 }
+                if (n > 0 || hf > 0) {                        // the previous bulk reduction must be done READING the staging tile
+                    if (r == 0) bulk_wait_read_all();
+                    bwd_bar_sync(5);
+                }
 #pragma unroll
-#ifndef GTA_BWD2_NORED
-                for (int u = 0; u < 8; ++u) red_add_v4(dst + (t3 * 8 + u) * 512, v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-#else
-                if (v[0] == 0x7fc12345u) dst[0] = 1.f;
-#endif
+                for (int u = 0; u < kHalf / 4; ++u)
+                    *reinterpret_cast<uint4*>(stage + u * 2048 + r * 16) = make_uint4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                fence_proxy_async_smem();
+                bwd_bar_sync(5);
+                if (r == 0) {
+                    bulk_reduce_add_f32(dst + hf * (kHalf / 4) * 512, stage, 128u * kHalf * 4u);
+                    bulk_commit_group();
+                }
             }
         }
+        if (r == 0) bulk_wait_all();
     } else {
         setmaxnreg_dec<56>();
         if (warp == 12) {
@@ -518,10 +550,10 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
             const uint32_t f0 = smem_u32(smem + L::kFix0), f1 = smem_u32(smem + L::kFix1);
             const uint32_t ds_sm = smem_u32(smem + L::kDS);
             mbar_wait(&bars[L::bFix], 0);
-            // streamed-tile stage of pair n: n % 3, its barrier parity (n / 3) & 1 — kept as counters (no division in the loop)
-            auto issue_s = [&](int s, int ph) {
-                const uint32_t g0 = smem_u32(smem + L::kStg0 + s * L::kTile);
-                mbar_wait(&bars[L::bFull + s], ph);
+            // ring slots of pair n: Q' n % 3, dO' n % 2, with the parities of their full barriers — kept as counters
+            auto issue_s = [&](int sq, int ph) {
+                const uint32_t g0 = smem_u32(smem + L::kStgQ + sq * L::kTile);
+                mbar_wait(&bars[L::bFullQ + sq], ph);
                 tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
@@ -531,8 +563,10 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
                 }
                 __syncwarp();
             };
-            auto issue_dp = [&](int s) {                      // (the stage is known to be full: S^T of the same pair was issued before)
-                const uint32_t g1 = smem_u32(smem + L::kStg1 + s * L::kTile);
+            auto issue_dp = [&](int so, int ph) {
+                const uint32_t g1 = smem_u32(smem + L::kStgO + so * L::kTile);
+                mbar_wait(&bars[L::bFullO + so], ph);
+                tc_fence_after();
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < D / 16; ++kk)
@@ -542,15 +576,16 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
                 __syncwarp();
             };
             issue_s(0, 0);
-            issue_dp(0);
-            int s = 0, s1 = 1, ph1 = 0;                       // s = n % 3; s1 = (n + 1) % 3 with parity ph1
+            issue_dp(0, 0);
+            int sq = 0, sq1 = 1, phq1 = 0;                    // sq = n % 3; sq1 = (n + 1) % 3 with parity phq1
+            int so = 0, so1 = 1, pho1 = 0;                    // so = n % 2; so1 = (n + 1) % 2 with parity pho1
 #pragma unroll 1
             for (int n = 0; n < N; ++n) {
-                const uint32_t g0 = smem_u32(smem + L::kStg0 + s * L::kTile), g1 = smem_u32(smem + L::kStg1 + s * L::kTile);
+                const uint32_t g0 = smem_u32(smem + L::kStgQ + sq * L::kTile), g1 = smem_u32(smem + L::kStgO + so * L::kTile);
                 if (n + 1 < N) {                             // next pair's S^T as soon as this pair's is in registers
                     mbar_wait(&bars[L::bSFree], n & 1);
                     tc_fence_after();
-                    issue_s(s1, ph1);
+                    issue_s(sq1, phq1);
                 }
                 mbar_wait(&bars[L::bPReady], n & 1);
                 tc_fence_after();
@@ -564,24 +599,28 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
                         umma_ts(tmem_base + kFTmemDV, tmem_base + kFTmemP + kk * 8, desc_mnmajor_sw64(g1, kk), idesc_kn, (kk > 0) ? 1u : accf);
+                    umma_commit(&bars[L::bEmptyO + so]);      // dO'_n has no reader left
+                    umma_commit(&bars[L::bPFree]);            // ... and P^T may be overwritten
                 }
                 __syncwarp();
                 if (n + 1 < N) {                             // dP^T of the next pair reuses the dQ' columns
                     mbar_wait(&bars[L::bDQFree], n & 1);
                     tc_fence_after();
-                    issue_dp(s1);
+                    issue_dp(so1, pho1);
                 }
                 if (elect_one()) {
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
                         umma_ss(tmem_base + kFTmemDK, desc_p_sw128(ds_sm, kk), desc_mnmajor_sw64(g0, kk), idesc_kn, (kk > 0) ? 1u : accf);
-                    umma_commit(&bars[L::bEmpty + s]);
+                    umma_commit(&bars[L::bEmptyQ + sq]);
                     umma_commit(&bars[L::bPdFree]);
                     if (n == N - 1) umma_commit(&bars[L::bDone]);
                 }
                 __syncwarp();
-                s = s1;
-                if (++s1 == L::kStages) { s1 = 0; ph1 ^= 1; }
+                sq = sq1;
+                if (++sq1 == L::kStagesQ) { sq1 = 0; phq1 ^= 1; }
+                so = so1;
+                if (++so1 == L::kStagesO) { so1 = 0; pho1 ^= 1; }
             }
         } else if (warp == 13) {
             // ======================================================= bulk-copy producer
@@ -590,18 +629,24 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
                 bulk_g2s(smem + L::kFix0, fix0, L::kTile, &bars[L::bFix]);
                 bulk_g2s(smem + L::kFix1, fix1, L::kTile, &bars[L::bFix]);
             }
-            int s = 0, ph = 1;                                // stage n % 3; parity of the (n / 3 - 1)-th completion of its empty barrier
+            int sq = 0, phq = 1, so = 0, pho = 1;             // ring slots; parities of the previous completion of their empty barriers
 #pragma unroll 1
             for (int n = 0; n < N; ++n) {
                 const int qi = qtile(n);
-                if (n >= L::kStages) mbar_wait(&bars[L::bEmpty + s], ph);
+                if (n >= L::kStagesQ) mbar_wait(&bars[L::bEmptyQ + sq], phq);
                 if (lane == 0) {
-                    mbar_arrive_expect_tx(&bars[L::bFull + s], 2 * L::kTile);
-                    bulk_g2s(smem + L::kStg0 + s * L::kTile, stg0 + static_cast<size_t>(qi) * L::kTile, L::kTile, &bars[L::bFull + s]);
-                    bulk_g2s(smem + L::kStg1 + s * L::kTile, stg1 + static_cast<size_t>(qi) * L::kTile, L::kTile, &bars[L::bFull + s]);
+                    mbar_arrive_expect_tx(&bars[L::bFullQ + sq], L::kTile);
+                    bulk_g2s(smem + L::kStgQ + sq * L::kTile, stg0 + static_cast<size_t>(qi) * L::kTile, L::kTile, &bars[L::bFullQ + sq]);
                 }
                 __syncwarp();
-                if (++s == L::kStages) { s = 0; ph ^= 1; }
+                if (n >= L::kStagesO) mbar_wait(&bars[L::bEmptyO + so], pho);
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&bars[L::bFullO + so], L::kTile);
+                    bulk_g2s(smem + L::kStgO + so * L::kTile, stg1 + static_cast<size_t>(qi) * L::kTile, L::kTile, &bars[L::bFullO + so]);
+                }
+                __syncwarp();
+                if (++sq == L::kStagesQ) { sq = 0; phq ^= 1; }
+                if (++so == L::kStagesO) { so = 0; pho ^= 1; }
             }
         }
     }

@@ -43,7 +43,7 @@ def main():
     for i, lab in ((1, "wait for S^T"), (12, "  of the next: tcgen05.ld S"), (2, "tcgen05.ld S + exp2 + pack P"), (3, "wait P^T/dS^T free + tcgen05.st P"),
                    (4, "wait for dP^T"), (5, "tcgen05.ld dP + dS + st.shared + arrive"), (7, "next-tile statistics + barrier")):
         print(f"    {lab:42s} {(d[:, i] / n).mean():7.0f} clk per tile")
-    print(f"    epilogue: wait for the last MMAs {d[:, 9].mean():.0f}, drain to shared memory {d[:, 10].mean():.0f}, rotate + store {d[:, 11].mean():.0f} clk per CTA")
+    print(f"    epilogue: operand prefetch {d[:, 13].mean():.0f} + wait for the last MMAs {(d[:, 9] - d[:, 13]).mean():.0f}, drain to shared memory {d[:, 10].mean():.0f}, rotate + store {d[:, 11].mean():.0f} clk per CTA")
 
 
 if __name__ == "__main__":

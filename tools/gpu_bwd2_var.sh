@@ -8,8 +8,19 @@ timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "backward"
 for v in ${VARIANTS:-""}; do
   [ "$v" = "main" ] && v=""
   echo "== variant libgta_b200$v.so"
-  for w in ${WL:-"msn_enc:64 clevr_dec:32"}; do
+  for w in ${WL:-msn_enc:64 clevr_dec:32}; do
     GTA_B200_LIB=$PWD/gta_b200/libgta_b200$v.so timeout 200 python tools/bwd_bench.py ${w%%:*} ${w##*:} | cut -c1-110
     GTA_B200_LIB=$PWD/gta_b200/libgta_b200$v.so timeout 200 python tools/bwd2_phase.py ${w%%:*} ${w##*:}
   done
 done
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"bwd|rotate|delta" -c 40 --csv --log-file gpurun_out/launches_bwd2.csv python tools/bwd_bench.py msn_enc 64 > /dev/null 2>&1
+python - <<'PY'
+import csv, collections
+rows = [l for l in open('gpurun_out/launches_bwd2.csv') if l.startswith('"')]
+r = list(csv.reader(rows)); h = r[0]; ki = h.index('Kernel Name'); vi = h.index('Metric Value')
+d = collections.defaultdict(list)
+for x in r[1:]:
+    try: d[x[ki][:70]].append(float(x[vi].replace(',', '')))
+    except Exception: pass
+for k, v in d.items(): print(f"{k:72s} n={len(v):3d} avg {sum(v)/len(v)/1e3:9.1f} us")
+PY
