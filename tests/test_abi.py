@@ -74,7 +74,9 @@ def test_backward_and_probs_argument_validation():
     bp.fwd.reps = _lib.GtaReps(*([0x1000] * 6), None, 0x1000, 0x1000)
     assert l.gta_attn_bwd(ctypes.byref(bp), None) == -3 and "no fused backward" in l.gta_last_error().decode()
     assert l.gta_attn_bwd(None, None) == -1
-    assert l.gta_attn_bwd_workspace_bytes(1, 2, 16, 16, 32) == 2 * 2 * 8192 + 2 * 2 * 8192 + 1024
+    # Q' and dO' images, K' | V' images, delta, and (head dims <= 96: the fused kernel) the fp32 dQ' accumulation tiles
+    assert l.gta_attn_bwd_workspace_bytes(1, 2, 16, 16, 32) == 2 * 2 * 8192 + 2 * 2 * 8192 + 1024 + 2 * 128 * 32 * 4
+    assert l.gta_attn_bwd_workspace_bytes(1, 2, 16, 16, 128) == 2 * 2 * 32768 + 2 * 2 * 32768 + 1024
     p = _params()
     assert l.gta_attn_probs(ctypes.byref(p), None, None) == -1 and "lse" in l.gta_last_error().decode()
     assert l.gta_attn_probs_workspace_bytes(1, 2, 16, 16, 32) == 2 * 4096
