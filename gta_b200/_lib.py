@@ -59,6 +59,7 @@ SYMBOLS = {
     "gta_attn_fwd": (c_int, [POINTER(GtaAttnParams), c_void_p]),
     "gta_attn_fwd_pipeline": (c_int, [POINTER(GtaAttnParams)]),
     "gta_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "gta_attn_bwd_workspace_bytes_p": (c_size_t, [POINTER(GtaAttnParams)]),
     "gta_attn_bwd": (c_int, [POINTER(GtaAttnBwdParams), c_void_p]),
     "gta_attn_probs_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "gta_attn_probs": (c_int, [POINTER(GtaAttnParams), c_void_p, c_void_p]),

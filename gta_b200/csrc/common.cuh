@@ -24,7 +24,11 @@ int launch_se3_inverse(const float* extr, int64_t n, float* inv, cudaStream_t st
 int launch_t2_mats(const float* coord, int64_t n, float* mats, float* inv, cudaStream_t st);
 
 size_t attn_bwd_workspace_bytes(int B, int H, int Tq, int Tk, int D);
-int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st);
+// delta_dout: the gradient the delta kernel pairs with fwd.out (the generic path stages a rotated dout but takes delta from
+// the un-rotated pair); nullptr = bp.dout
+int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st, const void* delta_dout = nullptr);
+size_t generic_bwd_workspace_bytes(const GtaAttnParams& p);
+int launch_attn_bwd_generic(const GtaAttnBwdParams& bp, cudaStream_t st);
 
 // Generic path (gta_generic.cu): t2 block, euclid_sim, head layouts with blocks that are not multiples of 8.
 bool attn_needs_generic(const GtaAttnParams& p);

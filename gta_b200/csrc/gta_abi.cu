@@ -112,6 +112,10 @@ int gta_attn_fwd(const GtaAttnParams* p, void* stream) {
 }
 
 size_t gta_attn_bwd_workspace_bytes(int B, int H, int Tq, int Tk, int D) { return attn_bwd_workspace_bytes(B, H, Tq, Tk, D); }
+size_t gta_attn_bwd_workspace_bytes_p(const GtaAttnParams* p) {
+    if (!p) return 0;
+    return attn_needs_generic(*p) ? generic_bwd_workspace_bytes(*p) : attn_bwd_workspace_bytes(p->B, p->H, p->Tq, p->Tk, p->D);
+}
 
 int gta_attn_bwd(const GtaAttnBwdParams* p, void* stream) {
     if (!p) return set_error(GTA_ERR_INVALID, "null params");

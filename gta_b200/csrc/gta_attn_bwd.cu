@@ -539,10 +539,10 @@ static int launch_bwd_t(const BwdArgs& a, int D, cudaStream_t st) {
     return set_error(GTA_ERR_UNSUPPORTED, "head dim %d", D);
 }
 
-int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st) {
+int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st, const void* delta_dout) {
     const GtaAttnParams& p = bp.fwd;
-    if (attn_needs_generic(p))
-        return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_bwd: the t2 / euclid_sim / unaligned-block configurations have no fused backward");
+    if (attn_needs_generic(p)) return launch_attn_bwd_generic(bp, st);   // t2 block / unaligned blocks (euclid_sim: unsupported)
+    if (!delta_dout) delta_dout = bp.dout;
     if (p.out_dtype != p.in_dtype) return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_bwd: out/dout must have the dtype of q/k/v");
     if (!p.lse || !bp.dout || !bp.dq || !bp.dk || !bp.dv) return set_error(GTA_ERR_INVALID, "gta_attn_bwd: null lse/dout/dq/dk/dv");
     const size_t need = attn_bwd_workspace_bytes(p.B, p.H, p.Tq, p.Tk, p.D);
@@ -573,9 +573,9 @@ int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st) {
         const int64_t want = (rows * 16 + 255) / 256;
         const unsigned nb = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
         float* dtc = p.se3 ? bp.dtrans_coeff : nullptr;
-        if (bf) bwd_delta_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p.out), static_cast<const __nv_bfloat16*>(bp.dout),
+        if (bf) bwd_delta_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(p.out), static_cast<const __nv_bfloat16*>(delta_dout),
                                                                     delta, dtc, p.reps.se3_q, p.B, p.Tq, p.H, p.D, p.Nq, p.Tq / p.Nq, p.triv, p.se3, p.v_transform);
-        else bwd_delta_kernel<float><<<nb, 256, 0, st>>>(static_cast<const float*>(p.out), static_cast<const float*>(bp.dout), delta, dtc,
+        else bwd_delta_kernel<float><<<nb, 256, 0, st>>>(static_cast<const float*>(p.out), static_cast<const float*>(delta_dout), delta, dtc,
                                                          p.reps.se3_q, p.B, p.Tq, p.H, p.D, p.Nq, p.Tq / p.Nq, p.triv, p.se3, p.v_transform);
     }
     rc = check_launch("gta_attn_bwd (staging)");

@@ -8,6 +8,8 @@
 // euclid_sim (EuclidAttnFn, source/layers.py:213-224): sim = q'.k' - |q'|^2/2 - |k'|^2/2.  The -|q'|^2/2 term is constant
 // along the softmax axis and cancels; -|k'|^2/2 is folded into the QK product through two extra operand columns
 // (k'[D] = hi, k'[D+1] = residual of -|k'|^2/2, q'[D] = q'[D+1] = 1), the head dim being padded by 32.
+#include <algorithm>
+
 #include "common.cuh"
 #include "reps.cuh"
 
@@ -31,6 +33,7 @@ struct GenArgs {
     int mode;                  // RepMode
     int rotate;                // 0: copy (v_transform = False)
     int ones;                  // euclid, query side: columns D, D+1 = 1
+    int out_bthd;              // modes Q/KV: write [B,T,H,Da] instead of [B,H,T,Da] (backward: dO' in the layout of dout)
 };
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
@@ -52,7 +55,7 @@ __device__ float gen_element(const GenArgs& a, int e, size_t view, size_t tok, f
         if (!g.euclid) {                       // 4-vectors, (M * scale_mask(tc)) or its transpose (gta.py:160-167,255-257)
             const int base = e - (e1 & 3), i = e1 & 3;
             const float x0 = ld(base), x1 = ld(base + 1), x2 = ld(base + 2), x3 = ld(base + 3);
-            if (mode == kModeQ) {
+            if (mode == kModeQ || mode == kModeKVT) {        // transpose of (M * scale_mask(tc))
                 if (i < 3) return fmaf(M[i], x0, fmaf(M[4 + i], x1, M[8 + i] * x2));
                 return fmaf(tc, fmaf(M[3], x0, fmaf(M[7], x1, M[11] * x2)), M[15] * x3);
             }
@@ -68,7 +71,7 @@ __device__ float gen_element(const GenArgs& a, int e, size_t view, size_t tok, f
     if (e2 < g.so3) {                          // [3 | 5] groups, Wigner D_1 / D_2 (gta.py:182-201,259-268)
         const float* W = a.so3m + view * 34;
         const int i = e2 & 7, base = e - i;
-        const bool tr = mode == kModeOut;
+        const bool tr = mode == kModeOut || mode == kModeKVT;
         float s = 0.f;
         if (i < 3) {
             for (int j = 0; j < 3; ++j) s = fmaf(tr ? W[j * 3 + i] : W[i * 3 + j], ld(base + j), s);
@@ -82,7 +85,7 @@ __device__ float gen_element(const GenArgs& a, int e, size_t view, size_t tok, f
     if (e3 < g.so2) {                          // pairs rotated by the token's angles (gta.py:203-219,269-271)
         const int pr = e3 >> 1, i = e3 & 1, base = e - i;
         const float* cs = a.so2cs + (tok * a.C + pr) * 2;
-        const float c = cs[0], s = mode == kModeOut ? -cs[1] : cs[1];
+        const float c = cs[0], s = (mode == kModeOut || mode == kModeKVT) ? -cs[1] : cs[1];
         const float x0 = ld(base), x1 = ld(base + 1);
         return i == 0 ? fmaf(c, x0, -s * x1) : fmaf(s, x0, c * x1);
     }
@@ -92,6 +95,7 @@ __device__ float gen_element(const GenArgs& a, int e, size_t view, size_t tok, f
         const float x0 = ld(base), x1 = ld(base + 1), x2 = ld(base + 2);
         if (mode == kModeQ) return i == 0 ? fmaf(-px, x2, x0) : (i == 1 ? fmaf(-py, x2, x1) : x2);   // (T^-1)^T
         if (mode == kModeKV) return i == 2 ? fmaf(px, x0, fmaf(py, x1, x2)) : (i == 0 ? x0 : x1);    // T
+        if (mode == kModeKVT) return i == 0 ? fmaf(px, x2, x0) : (i == 1 ? fmaf(py, x2, x1) : x2);   // T^T (backward: dk = rho_k^T dk')
         return i == 2 ? fmaf(-px, x0, fmaf(-py, x1, x2)) : (i == 0 ? x0 : x1);                      // T^-1
     }
 }
@@ -117,7 +121,8 @@ __global__ void gen_rotate_in_kernel(const GenArgs a) {
         else y = gen_element(a, e, static_cast<size_t>(b) * a.N + t / a.tpv, static_cast<size_t>(b) * a.T + t,
                              a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f, ld);
     }
-    reinterpret_cast<TStore*>(a.out)[i] = from_f32<TStore>(y);
+    const int64_t o = a.out_bthd ? ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.Da + e : i;
+    reinterpret_cast<TStore*>(a.out)[o] = from_f32<TStore>(y);
 }
 
 // euclid: k'[D], k'[D+1] = -|k'|^2/2 as value + residual in the storage type (one thread per key row, on the
@@ -135,8 +140,8 @@ __global__ void gen_key_bias_kernel(TStore* __restrict__ kt, int64_t rows, int D
     row[D + 1] = from_f32<TStore>(s - to_f32<TStore>(hi));
 }
 
-// mode Out: fp32 [B,T,H,Da] -> [B,T,H,D] (TOut) with rho_q^{-1} applied.
-template <typename TOut>
+// mode Out (or, backward, KVT): [B,T,H,Da] (TIn; fp32 for the forward's O') -> [B,T,H,D] (TOut) with rho_q^{-1} (rho_k^T) applied.
+template <typename TIn, typename TOut>
 __global__ void gen_rotate_out_kernel(const GenArgs a) {
     const int64_t total = static_cast<int64_t>(a.B) * a.T * a.H * a.D;
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -146,8 +151,8 @@ __global__ void gen_rotate_out_kernel(const GenArgs a) {
     const int h = static_cast<int>(r % a.H); r /= a.H;
     const int t = static_cast<int>(r % a.T);
     const int b = static_cast<int>(r / a.T);
-    const float* row = reinterpret_cast<const float*>(a.x) + ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.Da;
-    auto ld = [&](int idx) { return row[idx]; };
+    const TIn* row = reinterpret_cast<const TIn*>(a.x) + ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.Da;
+    auto ld = [&](int idx) { return to_f32<TIn>(row[idx]); };
     float y;
     if (!a.rotate) y = ld(e);
     else y = gen_element(a, e, static_cast<size_t>(b) * a.N + t / a.tpv, static_cast<size_t>(b) * a.T + t,
@@ -208,6 +213,7 @@ static GenArgs make_gen_args(const GtaAttnParams& p, int which /*0 q, 1 k, 2 v, 
     a.tc_ptr = p.trans_coeff;
     a.rotate = (which < 2) || p.v_transform;
     a.ones = (which == 0 && p.euclid) ? 1 : 0;
+    a.out_bthd = 0;
     return a;
 }
 
@@ -259,9 +265,146 @@ int launch_attn_fwd_generic(const GtaAttnParams& p, cudaStream_t st) {
     o.out = p.out;
     const int64_t total = static_cast<int64_t>(p.B) * p.Tq * p.H * p.D;
     const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
-    if (p.out_dtype == GTA_DTYPE_BF16) gen_rotate_out_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(o);
-    else gen_rotate_out_kernel<float><<<blocks, 256, 0, st>>>(o);
+    if (p.out_dtype == GTA_DTYPE_BF16) gen_rotate_out_kernel<float, __nv_bfloat16><<<blocks, 256, 0, st>>>(o);
+    else gen_rotate_out_kernel<float, float><<<blocks, 256, 0, st>>>(o);
     return check_launch("gta_attn_fwd (generic output rep)");
+}
+
+// ------------------------------------------------------------------------------------------------ generic backward
+// The reps are constant linear maps, so the backward of the generic path is the forward's scheme run around the
+// tensor-core backward (gta_attn_bwd.cu / gta_attn_bwd2.cu) on dense operands with an all-trivial head layout:
+//   q', k', v' (as in the forward), dO' = rho_q^{-T} dO  ->  dQ', dK', dV'  ->  dq = rho_q^{-1} dQ', dk = rho_k^T dK', dv = rho_k^T dV'.
+// delta = rowsum(dO * O) is invariant under the output rep and is taken from the un-rotated pair.  d(trans_coeff): the four
+// per-4-vector terms of the SE(3) block (query, key, value, output side), one element-wise reduction kernel.
+// Not for euclid_sim (its forward has no log-sum-exp output).
+struct GenDtcArgs {
+    const void* raw; int64_t sb, sh, st;     // raw input rows (q, k or v), strided [B,H,T,D]; part 3: O [B,T,H,D]
+    const void* g;                           // un-rotated gradient [B,T,H,D] contiguous (dQ', dK', dV'); part 3: dO
+    const float* se3m;                       // [B,N,16]
+    float* dtc;
+    int B, H, T, D, N, tpv, triv, se3, part; // part 0: query side, 1/2: key / value side, 3: output side
+};
+
+template <typename T>
+__global__ void gen_dtc_kernel(const GenDtcArgs a) {
+    const int nv = a.se3 >> 2;
+    const int64_t total = static_cast<int64_t>(a.B) * a.T * a.H * nv;
+    float part = 0.f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int v4 = static_cast<int>(i % nv);
+        int64_t r = i / nv;
+        const int h = static_cast<int>(r % a.H); r /= a.H;
+        const int t = static_cast<int>(r % a.T);
+        const int b = static_cast<int>(r / a.T);
+        const float* M = a.se3m + (static_cast<size_t>(b) * a.N + t / a.tpv) * 16;
+        const T* g = reinterpret_cast<const T*>(a.g) + ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.D + a.triv + 4 * v4;
+        const T* y = a.part == 3 ? reinterpret_cast<const T*>(a.raw) + ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.D + a.triv + 4 * v4
+                                 : reinterpret_cast<const T*>(a.raw) + b * a.sb + h * a.sh + t * a.st + a.triv + 4 * v4;
+        const float g0 = to_f32<T>(g[0]), g1 = to_f32<T>(g[1]), g2 = to_f32<T>(g[2]), g3 = to_f32<T>(g[3]);
+        if (a.part == 0) part += g3 * (M[3] * to_f32<T>(y[0]) + M[7] * to_f32<T>(y[1]) + M[11] * to_f32<T>(y[2]));
+        else if (a.part == 3) part += (g0 * M[3] + g1 * M[7] + g2 * M[11]) * to_f32<T>(y[3]) / M[15];
+        else part += (g0 * M[3] + g1 * M[7] + g2 * M[11]) * to_f32<T>(y[3]);
+    }
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        if (s != 0.f) atomicAdd(a.dtc, s);
+    }
+}
+
+struct GenBwdLayout {
+    size_t q, k, v, dout, dq, dk, dv, core, total;
+};
+static GenBwdLayout gen_bwd_layout(const GtaAttnParams& p) {
+    const size_t es = elt(p.in_dtype);
+    const size_t nq = align_up(static_cast<size_t>(p.B) * p.H * p.Tq * p.D * es), nk = align_up(static_cast<size_t>(p.B) * p.H * p.Tk * p.D * es);
+    GenBwdLayout l;
+    l.q = 0; l.k = l.q + nq; l.v = l.k + nk; l.dout = l.v + nk;
+    l.dq = l.dout + nq; l.dk = l.dq + nq; l.dv = l.dk + nk; l.core = l.dv + nk;
+    l.total = l.core + attn_bwd_workspace_bytes(p.B, p.H, p.Tq, p.Tk, p.D);
+    return l;
+}
+size_t generic_bwd_workspace_bytes(const GtaAttnParams& p) { return gen_bwd_layout(p).total; }
+
+int launch_attn_bwd_generic(const GtaAttnBwdParams& bp, cudaStream_t st) {
+    const GtaAttnParams& p = bp.fwd;
+    if (p.euclid) return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_bwd: euclid_sim has no fused backward");
+    if (p.out_dtype != p.in_dtype) return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_bwd: out/dout must have the dtype of q/k/v");
+    if (!p.lse || !bp.dout || !bp.dq || !bp.dk || !bp.dv) return set_error(GTA_ERR_INVALID, "gta_attn_bwd: null lse/dout/dq/dk/dv");
+    const GenBwdLayout l = gen_bwd_layout(p);
+    if (!bp.workspace || bp.workspace_bytes < l.total) return set_error(GTA_ERR_INVALID, "gta_attn_bwd: workspace too small (need %zu bytes)", l.total);
+    uint8_t* ws = static_cast<uint8_t*>(bp.workspace);
+    const bool bf = p.in_dtype == GTA_DTYPE_BF16;
+    for (int which = 0; which < 4; ++which) {          // q', k', v' and dO' = rho_q^{-T} dO (the map applied to q)
+        GenArgs a = make_gen_args(p, which == 3 ? 0 : which);
+        a.ones = 0;
+        if (which == 3) {
+            a.x = bp.dout;
+            a.sb = static_cast<int64_t>(p.Tq) * p.H * p.D; a.sh = p.D; a.st = static_cast<int64_t>(p.H) * p.D;
+            a.rotate = p.v_transform;
+            a.out_bthd = 1;
+        }
+        a.out = ws + (which == 0 ? l.q : (which == 1 ? l.k : (which == 2 ? l.v : l.dout)));
+        if (bf) launch_in<__nv_bfloat16, __nv_bfloat16>(a, st); else launch_in<float, float>(a, st);
+    }
+    int rc = check_launch("gta_attn_bwd (generic rep application)");
+    if (rc) return rc;
+
+    GtaAttnBwdParams c = bp;                           // the tensor-core backward on the prepared operands
+    GtaAttnParams& f = c.fwd;
+    f.q = ws + l.q; f.k = ws + l.k; f.v = ws + l.v;
+    f.q_stride_t = f.k_stride_t = f.v_stride_t = p.D;
+    f.q_stride_h = static_cast<int64_t>(p.Tq) * p.D; f.k_stride_h = f.v_stride_h = static_cast<int64_t>(p.Tk) * p.D;
+    f.q_stride_b = f.q_stride_h * p.H; f.k_stride_b = f.v_stride_b = f.k_stride_h * p.H;
+    f.triv = p.D; f.se3 = f.so3 = f.so2 = f.t2 = 0; f.euclid = 0;
+    f.reps = GtaReps{};
+    f.trans_coeff = nullptr;
+    f.v_transform = 0;
+    c.dout = ws + l.dout;
+    c.dq = ws + l.dq; c.dk = ws + l.dk; c.dv = ws + l.dv;
+    c.dtrans_coeff = nullptr;
+    c.workspace = ws + l.core;
+    c.workspace_bytes = bp.workspace_bytes - l.core;
+    rc = launch_attn_bwd(c, st, /*delta_dout=*/bp.dout);   // delta from the un-rotated (O, dO) pair
+    if (rc) return rc;
+
+    if (bp.dtrans_coeff && p.se3 > 0) {
+        for (int part = 0; part < 4; ++part) {
+            if (part >= 2 && !p.v_transform) continue;
+            GenDtcArgs d;
+            const bool qside = part == 0 || part == 3;
+            d.raw = part == 0 ? p.q : (part == 1 ? p.k : (part == 2 ? p.v : p.out));
+            d.sb = part == 0 ? p.q_stride_b : (part == 1 ? p.k_stride_b : p.v_stride_b);
+            d.sh = part == 0 ? p.q_stride_h : (part == 1 ? p.k_stride_h : p.v_stride_h);
+            d.st = part == 0 ? p.q_stride_t : (part == 1 ? p.k_stride_t : p.v_stride_t);
+            d.g = part == 0 ? static_cast<const void*>(ws + l.dq) : (part == 1 ? ws + l.dk : (part == 2 ? ws + l.dv : bp.dout));
+            d.se3m = qside ? p.reps.se3_q : p.reps.se3_k;
+            d.dtc = bp.dtrans_coeff;
+            d.B = p.B; d.H = p.H; d.D = p.D; d.T = qside ? p.Tq : p.Tk; d.N = qside ? p.Nq : p.Nk; d.tpv = d.T / d.N;
+            d.triv = p.triv; d.se3 = p.se3; d.part = part;
+            const int64_t total = static_cast<int64_t>(d.B) * d.T * d.H * (d.se3 >> 2);
+            const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 8));
+            if (bf) gen_dtc_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(d); else gen_dtc_kernel<float><<<blocks, 256, 0, st>>>(d);
+        }
+    }
+    for (int which = 0; which < 3; ++which) {          // dq = rho_q^{-1} dQ', dk = rho_k^T dK', dv = rho_k^T dV'
+        GenArgs o = make_gen_args(p, which == 0 ? 3 : which);
+        if (which > 0) o.mode = kModeKVT;
+        o.Da = p.D;
+        o.x = ws + (which == 0 ? l.dq : (which == 1 ? l.dk : l.dv));
+        o.out = which == 0 ? bp.dq : (which == 1 ? bp.dk : bp.dv);
+        o.rotate = (which < 2) || p.v_transform;
+        const int64_t total = static_cast<int64_t>(o.B) * o.T * o.H * o.D;
+        const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+        if (bf) gen_rotate_out_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>(o);
+        else gen_rotate_out_kernel<float, float><<<blocks, 256, 0, st>>>(o);
+    }
+    return check_launch("gta_attn_bwd (generic gradient reps)");
 }
 
 // attn[b,h,i,j] = exp(q'_i . k'_j * scale - lse[b,h,i]): 16x16 output tile per block, operands staged through shared memory.

@@ -264,8 +264,8 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
     grad_on = torch.is_grad_enabled()
     needs_grad = grad_on and (any(t.requires_grad for t in (q, k, v)) or
                               (torch.is_tensor(trans_coeff) and trans_coeff.requires_grad))
-    if needs_grad and (euclid or g("t2") or any(g(n) % 8 for n in ("triv", "se3", "so3", "so2"))):
-        return deleg("autograd through the t2 / euclid_sim / unaligned-block path")
+    if needs_grad and euclid:
+        return deleg("autograd through euclid_sim (its forward has no log-sum-exp output)")
     if g("so3") and not g("se3"):
         return deleg("so3 without se3 (undefined in the reference as well, SURVEY T5)")
     # softmax temperature: a closure variable of attn_fn.forward, never a keyword of this function

@@ -2,6 +2,7 @@
 else is the CUDA library.  All tensors must live on a CUDA device."""
 from __future__ import annotations
 
+import ctypes
 import dataclasses
 from typing import Dict, Optional
 
@@ -195,7 +196,7 @@ def gta_attention_bwd(dout: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: t
     bp.fwd = _params(q, k, v, o_c, reps, f_dims, trans_coeff, scale, v_transform, flags, lse.contiguous())
     bp.fwd.debug_clocks = _ptr(debug_clocks)
     bp.dout, bp.dq, bp.dk, bp.dv, bp.dtrans_coeff = _ptr(do_c), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dtc)
-    nbytes = lib().gta_attn_bwd_workspace_bytes(B, H, Tq, Tk, D)
+    nbytes = lib().gta_attn_bwd_workspace_bytes_p(ctypes.byref(bp.fwd))     # (covers the generic-path layouts: t2, unaligned blocks)
     ws = _workspace(dev, nbytes)
     bp.workspace = (ws.data_ptr() + 1023) // 1024 * 1024
     bp.workspace_bytes = nbytes

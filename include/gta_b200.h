@@ -160,6 +160,9 @@ typedef struct GtaAttnBwdParams {
 } GtaAttnBwdParams;
 
 size_t gta_attn_bwd_workspace_bytes(int B, int H, int Tq, int Tk, int D);
+/* ... of the call described by p->fwd-style parameters: also covers the generic-path layouts (t2 block, blocks that are not
+ * multiples of 8), whose backward runs the element-wise rep passes around the tensor-core backward on dense operands. */
+size_t gta_attn_bwd_workspace_bytes_p(const GtaAttnParams* p);
 int gta_attn_bwd(const GtaAttnBwdParams* p, void* stream);
 
 /* The attention map the reference returns as its second output (source/layers.py:207-211 `attn`, consumed only under

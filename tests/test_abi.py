@@ -72,7 +72,12 @@ def test_backward_and_probs_argument_validation():
     assert l.gta_attn_bwd(ctypes.byref(bp), None) == -1 and "lse" in l.gta_last_error().decode()
     bp.fwd = _params(se3=12, so3=8, so2=6, t2=6)
     bp.fwd.reps = _lib.GtaReps(*([0x1000] * 6), None, 0x1000, 0x1000)
-    assert l.gta_attn_bwd(ctypes.byref(bp), None) == -3 and "no fused backward" in l.gta_last_error().decode()
+    # generic-path layouts (t2 block / unaligned blocks) have a backward of their own; it validates its arguments first
+    assert l.gta_attn_bwd(ctypes.byref(bp), None) == -1 and "lse" in l.gta_last_error().decode()
+    assert l.gta_attn_bwd_workspace_bytes_p(ctypes.byref(bp.fwd)) == 7 * 2048 + l.gta_attn_bwd_workspace_bytes(1, 2, 16, 16, 32)
+    bp.fwd.euclid = 1
+    bp.fwd.reps.se3_qi = 0x1000
+    assert l.gta_attn_bwd(ctypes.byref(bp), None) == -3 and "euclid_sim" in l.gta_last_error().decode()
     assert l.gta_attn_bwd(None, None) == -1
     # Q' and dO' images, K' | V' images, delta, and (head dims <= 96: the fused kernel) the fp32 dQ' accumulation tiles
     assert l.gta_attn_bwd_workspace_bytes(1, 2, 16, 16, 32) == 2 * 2 * 8192 + 2 * 2 * 8192 + 1024 + 2 * 128 * 32 * 4

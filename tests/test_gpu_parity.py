@@ -495,7 +495,8 @@ def _grad_oracle(cfg, inp, tc, dout):
     if cfg.v_transform:
         has = lambda n: reps[n].transpose(-1, -2) if n in reps else None
         Ao = tp._scale_translation(reps["se3_qinv"], tcv) if cfg.dims()[1] else None
-        out = tp._apply_blocks(out, cfg, Ao, has("so3_d1_q"), has("so3_d2_q"), reps.get("so2_th_q"), True, cfg.n_q_views)
+        out = tp._apply_blocks(out, cfg, Ao, has("so3_d1_q"), has("so3_d2_q"), reps.get("so2_th_q"), True, cfg.n_q_views,
+                               reps.get("t2_qinv"))
     out.backward(dout.double())
     # d(trans_coeff) is a sum of four strongly cancelling parts (query, key, value and output side, e.g. 5.8 + 36.0 - 16.6
     # - 22.5 = 2.7): its error budget is relative to the sum of their magnitudes
@@ -528,7 +529,11 @@ def _grad_oracle(cfg, inp, tc, dout):
     (MSN_SO3, 3, 2, 40, 64, True, 1, torch.float32, 0.3, True),         # fp32 I/O (bf16 tensor-core math in the backward)
     (CLEVR, 3, 2, 853, 300, True, 1, torch.bfloat16, 0.01, True),       # CLEVR decoder shape (Tq = 2559, ragged everywhere)
     (MSN_SO3, 5, 5, 512, 256, True, 1, torch.bfloat16, 0.01, True),     # MSN decoder shape (Tq = 2560, Tk = 1280)
-], ids=["cfg1b", "msn_cross", "msn_enc", "clevr_dec", "clevr_novt", "msn_cross_f32", "clevr_dec_full", "msn_dec_full"])
+    (CLEVR_T2, 3, 2, 171, 300, True, 1, torch.bfloat16, 0.3, True),     # generic path: triv 2 | se3 32 | t2 30 (runs/clevrtr/GTA/gta_t2)
+    (MSN_T2, 2, 2, 100, 100, False, 2, torch.bfloat16, 0.3, True),      # generic path: se3 48 | t2 48 (runs/msn/GTA/gta_t2)
+    (CLEVR_T2, 2, 2, 150, 150, False, 1, torch.float32, 0.5, False),    # generic path, fp32 I/O, v_transform = False
+], ids=["cfg1b", "msn_cross", "msn_enc", "clevr_dec", "clevr_novt", "msn_cross_f32", "clevr_dec_full", "msn_dec_full",
+        "clevr_t2_cross", "msn_t2", "clevr_t2_f32_novt"])
 def test_fused_backward_matches_autograd_oracle(case):
     """dq, dk, dv and d(trans_coeff) of the fused backward, through the public drop-in under autograd, against fp64
     autograd of the oracle on the same (rounded) inputs.  bf16 tensor-core math: errors relative to the gradient scale."""
@@ -547,7 +552,10 @@ def test_fused_backward_matches_autograd_oracle(case):
     if cfg.so3:
         extras.update({"so3rep_q": [r["so3_d1_q"].cuda(), r["so3_d2_q"].cuda()],
                        "so3rep_k": [r["so3_d1_k"].cuda(), r["so3_d2_k"].cuda()]})
-    extras.update({"so2rep_q": tp.so2_mats(r["so2_th_q"]).cuda(), "so2rep_k": tp.so2_mats(r["so2_th_k"]).cuda()})
+    if cfg.so2:
+        extras.update({"so2rep_q": tp.so2_mats(r["so2_th_q"]).cuda(), "so2rep_k": tp.so2_mats(r["so2_th_k"]).cuda()})
+    if cfg.t2_dim():        # reference-format [B,T,3,3] matrices (make_T2mats, encoder.py:208-215)
+        extras.update({"t2rep_q": r["t2_q"].cuda(), "t2rep_k": r["t2_k"].cuda(), "inv_t2rep_q": r["t2_qinv"].cuda()})
 
     class AttnFn:
         scale = cfg.head_dim ** -0.5
@@ -607,7 +615,16 @@ def test_backward_fused_kernel_matches_kernel_pair(case):
     fused = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc)
     again = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc)
     pair = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=_lib.GTA_FLAG_BWD_SPLIT)
+    # the run-time-layout epilogue (head layouts without a compile-time instantiation) on the same call
+    rt = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=_lib.GTA_FLAG_RUNTIME_LAYOUT)
     torch.cuda.synchronize()
+    for name, a, b in zip(("dq", "dk", "dv"), fused[:3], rt[:3]):
+        if name == "dq":
+            assert float((a.float() - b.float()).abs().max()) <= 1e-2 * float(b.float().abs().max()) + 1e-4
+        else:
+            assert torch.equal(a, b), name + " (run-time layout epilogue)"
+    if fused[3] is not None:      # (the compile-time epilogue takes the raw w components from the bf16 K'/V' images)
+        assert abs(float(fused[3]) - float(rt[3])) <= 1e-2 * max(1.0, abs(float(rt[3])))
     for name, a, a2, b in zip(("dq", "dk", "dv"), fused[:3], again[:3], pair[:3]):
         assert torch.isfinite(a.float()).all(), name
         scale_ = float(b.float().abs().max())
