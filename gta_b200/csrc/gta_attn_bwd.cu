@@ -460,36 +460,39 @@ template <typename T>
 __global__ void bwd_delta_kernel(const T* __restrict__ out, const T* __restrict__ dout, float* __restrict__ delta,
                                  float* dtc, const float* __restrict__ se3_q, int B, int Tq, int H, int D, int Nq, int tpvq,
                                  int triv, int se3, int v_transform) {
-    const int64_t total = static_cast<int64_t>(B) * Tq * H;
-    const int c = threadIdx.x & 15;
+    // rows = (b, t, h) in memory order; 32-bit index arithmetic (the launcher guarantees B*Tq*H < 2^31): the 64-bit
+    // divisions of a first version made this HBM pass instruction-bound (2.2 TB/s)
+    const uint32_t total = static_cast<uint32_t>(B) * Tq * H;
+    const uint32_t c = threadIdx.x & 15;
+    const bool tc_lane = dtc && v_transform && se3 && static_cast<int>(c * 8) >= triv && static_cast<int>(c * 8) < triv + se3;
     float part = 0.f;
     // grid-stride over groups of 16 rows per block: the trans_coeff partial sums stay in registers and cost ONE atomic per
     // block at the end (one atomic per warp on a single address serialised in L2: +0.25 ms at the MSN shape)
-    for (int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4; row < ((total + 15) & ~15LL);
-         row += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 4) {
-    float acc = 0.f;
-    if (row < total && c * 8 < D) {
-        const int64_t bt = row / H;
-        const int t = static_cast<int>(bt % Tq), b = static_cast<int>(bt / Tq);
-        float xo[8], xg[8];
-        load_chunk<T>(out + row * D + c * 8, xo);
-        load_chunk<T>(dout + row * D + c * 8, xg);
+    const uint32_t stride = (gridDim.x * blockDim.x) >> 4;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; row < ((total + 15u) & ~15u); row += stride) {
+        float acc = 0.f;
+        if (row < total && static_cast<int>(c * 8) < D) {
+            float xo[8], xg[8];
+            load_chunk<T>(out + static_cast<size_t>(row) * D + c * 8, xo);
+            load_chunk<T>(dout + static_cast<size_t>(row) * D + c * 8, xg);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc = fmaf(xo[u], xg[u], acc);
-        if (dtc && v_transform && se3 && c * 8 >= triv && c * 8 < triv + se3) {
-            const float* M = se3_q + (static_cast<size_t>(b) * Nq + t / tpvq) * 16;
+            for (int u = 0; u < 8; ++u) acc = fmaf(xo[u], xg[u], acc);
+            if (tc_lane) {
+                const uint32_t bt = row / H;
+                const uint32_t b = bt / Tq, t = bt - b * Tq;
+                const float* M = se3_q + (static_cast<size_t>(b) * Nq + t / tpvq) * 16;
 #pragma unroll
-            for (int v4 = 0; v4 < 2; ++v4)
-                part += (xg[4 * v4] * M[3] + xg[4 * v4 + 1] * M[7] + xg[4 * v4 + 2] * M[11]) * xo[4 * v4 + 3] / M[15];
+                for (int v4 = 0; v4 < 2; ++v4)
+                    part += (xg[4 * v4] * M[3] + xg[4 * v4 + 1] * M[7] + xg[4 * v4 + 2] * M[11]) * xo[4 * v4 + 3] / M[15];
+            }
         }
-    }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (row < total && c == 0) {
-        const int h = static_cast<int>(row % H);
-        const int64_t bt = row / H;
-        delta[(static_cast<int64_t>(bt / Tq) * H + h) * Tq + bt % Tq] = acc;
-    }
+        for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (row < total && c == 0) {
+            const uint32_t bt = row / H, h = row - bt * H;
+            const uint32_t b = bt / Tq, t = bt - b * Tq;
+            delta[(static_cast<size_t>(b) * H + h) * Tq + t] = acc;
+        }
     }
     if (dtc) {
         __shared__ float red[8];
@@ -570,6 +573,7 @@ int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st, const void* del
     if (rc) return rc;
     {
         const int64_t rows = static_cast<int64_t>(p.B) * p.Tq * p.H;
+        if (rows >= (1LL << 31) - 16) return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_bwd: B*Tq*H must be below 2^31");
         const int64_t want = (rows * 16 + 255) / 256;
         const unsigned nb = static_cast<unsigned>(want < 148 * 16 ? want : 148 * 16);
         float* dtc = p.se3 ? bp.dtrans_coeff : nullptr;

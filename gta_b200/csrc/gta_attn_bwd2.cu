@@ -658,75 +658,76 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
     }
 }
 
-// dq = rho_q^{-1} dQ' from the fp32 accumulation tiles (+ the query-side trans_coeff term): thread = query row, the rotated
-// rows are staged in shared memory and written out coalesced.  HBM-bound: 4 D bytes read + sizeof(TOut) D written per row.
+// dq = rho_q^{-1} dQ' from the fp32 accumulation tiles (+ the query-side trans_coeff term).  HBM-bound: 4 D bytes read +
+// sizeof(TOut) D written per row.  The (row, 8-column chunk) walk of the fused kernel's epilogue: the chunk index is fastest
+// over the lanes inside a block type, so the accumulation tile ([D/4][128 rows][4 floats]), the token's angles, the raw q
+// chunks of the trans_coeff term and the output rows are all read / written in contiguous pieces by neighbouring lanes
+// (a thread-per-row version with a shared-memory transpose ran at 3.4 TB/s).
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(128) bwd_dq_finish_kernel(const BwdArgs a, const int D) {
-    extern __shared__ uint8_t fsm[];
     const int tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int r = threadIdx.x;
+    const int lane = threadIdx.x & 31, w4 = threadIdx.x >> 5;
     const size_t bh = static_cast<size_t>(b) * a.H + h;
-    const float* acc = a.dq_acc + (bh * a.ntq + tile) * (128u * D) + r * 4;
-    const int t = tile * 128 + r;
-    const bool valid = t < a.Tq;
-    const int tt = valid ? t : a.Tq - 1;
-    const size_t view = static_cast<size_t>(b) * a.Nq + tt / a.tpvq;
-    const float* se3 = a.se3_q + view * 16;
-    const float* so3 = a.so3_q + view * 34;
-    const float* so2 = a.so2_q + (static_cast<size_t>(b) * a.Tq + tt) * a.C * 2;
-    const int c_se3 = a.hd.triv >> 3, c_so3 = c_se3 + (a.hd.se3 >> 3);
+    const float* acc = a.dq_acc + (bh * a.ntq + tile) * (128u * D);
+    const int t0 = tile * 128;
+    const int K = D >> 3;
+    const int k1 = a.hd.triv >> 3, k2 = k1 + (a.hd.se3 >> 3), k3 = k2 + (a.hd.so3 >> 3);
     const float tc = a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f;
-    const TIn* raw = reinterpret_cast<const TIn*>(a.q) + b * a.q_sb + h * a.q_sh + static_cast<int64_t>(tt) * a.q_st;
-    const uint32_t pitch = D * sizeof(TOut) + (sizeof(TOut) == 2 ? 16 : 0);
-    uint8_t* stage_row = fsm + static_cast<size_t>(r) * pitch;
-    const bool want_tc = valid && a.dtc != nullptr && a.hd.se3 > 0;
+    const TIn* rawbase = reinterpret_cast<const TIn*>(a.q) + b * a.q_sb + h * a.q_sh;
+    TOut* gbase = reinterpret_cast<TOut*>(a.dq) + (static_cast<int64_t>(b) * a.Tq * a.H + h) * D;
+    const float* so2_b = a.so2_q + static_cast<size_t>(b) * a.Tq * a.C * 2;
+    const bool want_tc = a.dtc != nullptr && a.hd.se3 > 0;
+    int cached_view = -1;
     ViewReps vr;
-    load_view_reps(vr, a.hd, se3, so3);
-    const float* M = vr.M;
     float dtc_part = 0.f;
-    const int nch = D >> 3;
-    float4 n0 = __ldg(reinterpret_cast<const float4*>(acc));
-    float4 n1 = __ldg(reinterpret_cast<const float4*>(acc + 512));
 #pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-        float x[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-        if (c + 1 < nch) {
-            n0 = __ldg(reinterpret_cast<const float4*>(acc + (2 * c + 2) * 512));
-            n1 = __ldg(reinterpret_cast<const float4*>(acc + (2 * c + 3) * 512));
-        }
-        const So2Chunk sc = load_so2_chunk(so2, c, a.hd);
-        if (want_tc && c >= c_se3 && c < c_so3) {
-            // Q' = (E_q msk)^T q: d/dtc = g_3 (M_03 q_0 + M_13 q_1 + M_23 q_2) per SE(3) 4-vector
-            RawChunk<TIn> rc;
-            load_raw(raw + c * 8, rc);
-            float xin[8];
-            raw_to_f32(rc, xin);
-#pragma unroll
-            for (int v4 = 0; v4 < 2; ++v4) {
-                const float* g = x + 4 * v4;
-                const float* y = xin + 4 * v4;
-                dtc_part += g[3] * (M[3] * y[0] + M[7] * y[1] + M[11] * y[2]);
+    for (int k = 0; k < K; ++k) {
+        const int sg = k < k1 ? 0 : (k < k2 ? 1 : (k < k3 ? 2 : 3));
+        const int st = sg == 0 ? 0 : (sg == 1 ? k1 : (sg == 2 ? k2 : k3));
+        const int n_t = (sg == 0 ? k1 : (sg == 1 ? k2 : (sg == 2 ? k3 : K))) - st;
+        const int idx = lane + 32 * (k - st);
+        const int rr = idx / n_t;
+        const int ch = st + idx - rr * n_t;
+        const int row = w4 * 32 + rr;
+        const int t = t0 + row;
+        if (t >= a.Tq) continue;
+        const float4 xa = __ldg(reinterpret_cast<const float4*>(acc + (2 * ch) * 512 + row * 4));
+        const float4 xb = __ldg(reinterpret_cast<const float4*>(acc + (2 * ch + 1) * 512 + row * 4));
+        float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        if (sg == 1 || sg == 2) {
+            const int vrow = t / a.tpvq;
+            if (vrow != cached_view) {
+                cached_view = vrow;
+                load_view_reps(vr, a.hd, a.se3_q + (static_cast<size_t>(b) * a.Nq + vrow) * 16, a.so3_q + (static_cast<size_t>(b) * a.Nq + vrow) * 34);
             }
         }
-        apply_rep_chunk_pre<kModeOut>(x, c, a.hd, vr, sc, tc);
-        store_chunk<TOut>(reinterpret_cast<TOut*>(stage_row) + c * 8, x);
+        if (sg == 1) {
+            if (want_tc) {
+                // Q' = (E_q msk)^T q: d/dtc = g_3 (M_03 q_0 + M_13 q_1 + M_23 q_2) per SE(3) 4-vector
+                RawChunk<TIn> rc;
+                load_raw(rawbase + t * a.q_st + ch * 8, rc);
+                float xin[8];
+                raw_to_f32(rc, xin);
+#pragma unroll
+                for (int v4 = 0; v4 < 2; ++v4)
+                    dtc_part += x[4 * v4 + 3] * (vr.M[3] * xin[4 * v4] + vr.M[7] * xin[4 * v4 + 1] + vr.M[11] * xin[4 * v4 + 2]);
+            }
+            se3_apply(x, vr.M, tc);
+        } else if (sg == 2) {
+            so3_apply<true>(x, vr.W);
+        } else if (sg == 3) {
+            const So2Chunk sc = load_so2_chunk(so2_b + static_cast<size_t>(t) * a.C * 2, ch, a.hd);
+            const float cs8[8] = {sc.a.x, sc.a.y, sc.a.z, sc.a.w, sc.b.x, sc.b.y, sc.b.z, sc.b.w};
+            so2_apply<true>(x, cs8);
+        }
+        store_chunk<TOut>(gbase + static_cast<int64_t>(t) * a.H * D + ch * 8, x);
     }
-    __syncthreads();
-    const int pieces = D * static_cast<int>(sizeof(TOut)) / 16;
-    const int nrows = min(128, a.Tq - tile * 128);
-    TOut* gbase = reinterpret_cast<TOut*>(a.dq);
-    for (int idx = r; idx < nrows * pieces; idx += 128) {
-        const int row = idx / pieces, pc = idx - row * pieces;
-        const uint4 val = *reinterpret_cast<const uint4*>(fsm + static_cast<size_t>(row) * pitch + pc * 16);
-        TOut* grow = gbase + ((static_cast<int64_t>(b) * a.Tq + tile * 128 + row) * a.H + h) * D;
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(grow) + pc * 16) = val;
-    }
-    if (a.dtc && a.hd.se3 > 0) {
+    if (want_tc) {
         __shared__ float red[4];
         dtc_part = warp_sum(dtc_part);
-        if ((r & 31) == 0) red[r >> 5] = dtc_part;
+        if (lane == 0) red[w4] = dtc_part;
         __syncthreads();
-        if (r == 0) {
+        if (threadIdx.x == 0) {
             const float s = red[0] + red[1] + red[2] + red[3];
             if (s != 0.f) atomicAdd(a.dtc, s);
         }
@@ -749,10 +750,7 @@ static int launch_bwd_fused_d(const BwdArgs& a, cudaStream_t st) {
     e = cudaMemsetAsync(a.dq_acc, 0, bwd_dq_acc_bytes(a.B, a.H, a.Tq, D), st);
     if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
     kern<<<dim3(a.ntk, a.H, a.B), kFThreads, L::kBytes, st>>>(a);
-    const uint32_t pitch = D * sizeof(T) + (sizeof(T) == 2 ? 16 : 0);
-    e = cudaFuncSetAttribute(bwd_dq_finish_kernel<T, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(128 * pitch));
-    if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    bwd_dq_finish_kernel<T, T><<<dim3(a.ntq, a.H, a.B), 128, 128 * pitch, st>>>(a, D);
+    bwd_dq_finish_kernel<T, T><<<dim3(a.ntq, a.H, a.B), 128, 0, st>>>(a, D);
     return check_launch("gta_attn_bwd (fused)");
 }
 

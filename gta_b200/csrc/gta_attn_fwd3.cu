@@ -28,9 +28,6 @@ constexpr int kStagerThreads = 64;
 constexpr uint32_t k3TmemSA = 0, k3TmemSB = 128, k3TmemOA = 256, k3TmemOB = 384;
 constexpr float k3RescaleThreshold = 8.0f;   // log2 units
 // Fraction of the exponentials evaluated with poly_exp2x2 instead of MUFU.EX2: pairs with (i % DEN) < NUM.
-#ifndef GTA_EPI_HOIST
-#define GTA_EPI_HOIST 0
-#endif
 #ifndef GTA_POLY_NUM
 #define GTA_POLY_NUM 0
 #endif
@@ -252,30 +249,6 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
             //  before use and nothing has to stay live across the wait)
             const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
             const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
-#if GTA_EPI_HOIST
-            // the row's view matrices and first SO(2) chunk are requested BEFORE the wait for the last PV (the score registers
-            // are dead here, so 58 more live values cost nothing): their latency overlaps the wait
-            float M[16], W[34];
-            So2Chunk sc_first;
-            sc_first.a = make_float4(1.f, 0.f, 1.f, 0.f); sc_first.b = sc_first.a;
-            if (a.v_transform) {
-                if (c_so3 > c_se3) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 q4 = __ldg(reinterpret_cast<const float4*>(a.se3_q + view * 16) + i);
-                        M[4 * i] = q4.x; M[4 * i + 1] = q4.y; M[4 * i + 2] = q4.z; M[4 * i + 3] = q4.w;
-                    }
-                }
-                if (c_so2 > c_so3) {
-#pragma unroll
-                    for (int i = 0; i < 17; ++i) {
-                        const float2 q2 = __ldg(reinterpret_cast<const float2*>(a.so3_q + view * 34) + i);
-                        W[2 * i] = q2.x; W[2 * i + 1] = q2.y;
-                    }
-                }
-                if (c_so2 < D / 8) sc_first = load_so2_chunk(so2, c_so2, a.hd);
-            }
-#endif
             mbar_wait(&bars[L::bOFinal + X], cnt & 1);
             const long long d_t2 = dbg ? clock64() : 0;
             ++cnt;
@@ -318,14 +291,12 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
             long long e1 = 0, e2 = 0;
             if (a.v_transform) {
                 if (c_so3 > c_se3) {
-#if !GTA_EPI_HOIST
                     float M[16];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 q4 = __ldg(reinterpret_cast<const float4*>(a.se3_q + view * 16) + i);
                         M[4 * i] = q4.x; M[4 * i + 1] = q4.y; M[4 * i + 2] = q4.z; M[4 * i + 3] = q4.w;
                     }
-#endif
 #pragma unroll 1
                     for (int c = c_se3; c < c_so3; ++c) {
                         float x[8];
@@ -336,14 +307,12 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                 }
                 if (dbg) e1 = clock64();
                 if (c_so2 > c_so3) {
-#if !GTA_EPI_HOIST
                     float W[34];
 #pragma unroll
                     for (int i = 0; i < 17; ++i) {
                         const float2 q2 = __ldg(reinterpret_cast<const float2*>(a.so3_q + view * 34) + i);
                         W[2 * i] = q2.x; W[2 * i + 1] = q2.y;
                     }
-#endif
 #pragma unroll 1
                     for (int c = c_so3; c < c_so2; ++c) {
                         float x[8];
@@ -353,11 +322,7 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                     }
                 }
                 if (dbg) e2 = clock64();
-#if GTA_EPI_HOIST
-                So2Chunk sc_cur = sc_first;
-#else
                 So2Chunk sc_cur = load_so2_chunk(so2, c_so2, a.hd);
-#endif
 #pragma unroll 1
                 for (int c = c_so2; c < D / 8; ++c) {
                     So2Chunk sc_nxt = sc_cur;
