@@ -34,6 +34,9 @@ struct GenArgs {
     int rotate;                // 0: copy (v_transform = False)
     int ones;                  // euclid, query side: columns D, D+1 = 1
     int out_bthd;              // modes Q/KV: write [B,T,H,Da] instead of [B,H,T,Da] (backward: dO' in the layout of dout)
+    int se3_lin_t;             // euclid backward: the SE(3) block applies the TRANSPOSED 3x3 linear part of se3m (no translation)
+    int sub_trans;             // euclid backward: SE(3) block only, y = x - tc * translation column of se3m (every other element copied)
+    const void* bias_k;        // euclid backward, mode KVT: dense k' [B,H,T,Da]; the loaded gradient row becomes g[e] - g[D] * k'[e]
 };
 
 template <typename T> __device__ __forceinline__ float to_f32(T v);
@@ -50,6 +53,7 @@ __device__ float gen_element(const GenArgs& a, int e, size_t view, size_t tok, f
     const int mode = a.mode;
     if (e < g.triv) return ld(e);
     int e1 = e - g.triv;
+    if (a.sub_trans && e1 >= g.se3) return ld(e);
     if (e1 < g.se3) {
         const float* M = a.se3m + view * 16;
         if (!g.euclid) {                       // 4-vectors, (M * scale_mask(tc)) or its transpose (gta.py:160-167,255-257)
@@ -62,9 +66,11 @@ __device__ float gen_element(const GenArgs& a, int e, size_t view, size_t tok, f
             if (i < 3) return fmaf(M[4 * i], x0, fmaf(M[4 * i + 1], x1, fmaf(M[4 * i + 2], x2, M[4 * i + 3] * tc * x3)));
             return M[15] * x3;
         }
-        // euclid: homogenised 3-vectors, no transpose on the query side (gta.py:146-156,251-253)
+        // euclid: homogenised 3-vectors, no transpose on the query side (gta.py:146-156,251-253): y = A x + t * tc
         const int i = e1 % 3, base = e - i;
+        if (a.sub_trans) return ld(e) - M[4 * i + 3] * tc;
         const float x0 = ld(base), x1 = ld(base + 1), x2 = ld(base + 2);
+        if (a.se3_lin_t) return fmaf(M[i], x0, fmaf(M[4 + i], x1, M[8 + i] * x2));       // backward: A^T g
         return fmaf(M[4 * i], x0, fmaf(M[4 * i + 1], x1, fmaf(M[4 * i + 2], x2, M[4 * i + 3] * tc)));
     }
     int e2 = e1 - g.se3;
@@ -152,7 +158,10 @@ __global__ void gen_rotate_out_kernel(const GenArgs a) {
     const int t = static_cast<int>(r % a.T);
     const int b = static_cast<int>(r / a.T);
     const TIn* row = reinterpret_cast<const TIn*>(a.x) + ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.Da;
-    auto ld = [&](int idx) { return to_f32<TIn>(row[idx]); };
+    // euclid_sim: the bias -|k'|^2/2 sits in operand column D, so its gradient is g[D] and dk' = g[:D] - g[D] k'
+    const TIn* krow = a.bias_k ? reinterpret_cast<const TIn*>(a.bias_k) + ((static_cast<int64_t>(b) * a.H + h) * a.T + t) * a.Da : nullptr;
+    const float gb = krow ? to_f32<TIn>(row[a.D]) : 0.f;
+    auto ld = [&](int idx) { return krow ? fmaf(-gb, to_f32<TIn>(krow[idx]), to_f32<TIn>(row[idx])) : to_f32<TIn>(row[idx]); };
     float y;
     if (!a.rotate) y = ld(e);
     else y = gen_element(a, e, static_cast<size_t>(b) * a.N + t / a.tpv, static_cast<size_t>(b) * a.T + t,
@@ -214,6 +223,7 @@ static GenArgs make_gen_args(const GtaAttnParams& p, int which /*0 q, 1 k, 2 v, 
     a.rotate = (which < 2) || p.v_transform;
     a.ones = (which == 0 && p.euclid) ? 1 : 0;
     a.out_bthd = 0;
+    a.se3_lin_t = 0; a.sub_trans = 0; a.bias_k = nullptr;
     return a;
 }
 
@@ -226,7 +236,6 @@ static void launch_in(const GenArgs& a, cudaStream_t st) {
 int launch_attn_fwd_generic(const GtaAttnParams& p, cudaStream_t st) {
     const int Da = padded_dim(p);
     if (Da > 128) return set_error(GTA_ERR_UNSUPPORTED, "euclid_sim needs head dim + 32 <= 128");
-    if (p.euclid && p.lse) return set_error(GTA_ERR_UNSUPPORTED, "lse output is not defined for euclid_sim");
     const GenLayout l = gen_layout(p);
     uint8_t* ws = static_cast<uint8_t*>(p.workspace);
     const bool bf = p.in_dtype == GTA_DTYPE_BF16;
@@ -282,12 +291,15 @@ struct GenDtcArgs {
     const void* g;                           // un-rotated gradient [B,T,H,D] contiguous (dQ', dK', dV'); part 3: dO
     const float* se3m;                       // [B,N,16]
     float* dtc;
-    int B, H, T, D, N, tpv, triv, se3, part; // part 0: query side, 1/2: key / value side, 3: output side
+    int B, H, T, D, Dg, N, tpv, triv, se3, part; // part 0: query side, 1/2: key / value side, 3: output side; Dg: row pitch of g
+    int euclid;                              // homogenised 3-vectors: every term is the gradient dotted with the translation column
+    const void* bias_k; int Da;              // euclid, key side: dense k' [B,H,T,Da]; the gradient is g[e] - g[D] k'[e] (bias -|k'|^2/2)
 };
 
 template <typename T>
 __global__ void gen_dtc_kernel(const GenDtcArgs a) {
-    const int nv = a.se3 >> 2;
+    const int vlen = a.euclid ? 3 : 4;
+    const int nv = a.se3 / vlen;
     const int64_t total = static_cast<int64_t>(a.B) * a.T * a.H * nv;
     float part = 0.f;
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -297,10 +309,20 @@ __global__ void gen_dtc_kernel(const GenDtcArgs a) {
         const int t = static_cast<int>(r % a.T);
         const int b = static_cast<int>(r / a.T);
         const float* M = a.se3m + (static_cast<size_t>(b) * a.N + t / a.tpv) * 16;
-        const T* g = reinterpret_cast<const T*>(a.g) + ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.D + a.triv + 4 * v4;
+        const T* g = reinterpret_cast<const T*>(a.g) + ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.Dg + a.triv + vlen * v4;
+        float g0 = to_f32<T>(g[0]), g1 = to_f32<T>(g[1]), g2 = to_f32<T>(g[2]);
+        if (a.euclid) {                 // y = A x + t * tc  =>  d/dtc = g . t
+            if (a.bias_k) {
+                const T* kr = reinterpret_cast<const T*>(a.bias_k) + ((static_cast<int64_t>(b) * a.H + h) * a.T + t) * a.Da + a.triv + vlen * v4;
+                const float gb = to_f32<T>(g[a.D - a.triv - vlen * v4]);        // column D of the row
+                g0 = fmaf(-gb, to_f32<T>(kr[0]), g0); g1 = fmaf(-gb, to_f32<T>(kr[1]), g1); g2 = fmaf(-gb, to_f32<T>(kr[2]), g2);
+            }
+            part += g0 * M[3] + g1 * M[7] + g2 * M[11];
+            continue;
+        }
+        const float g3 = to_f32<T>(g[3]);
         const T* y = a.part == 3 ? reinterpret_cast<const T*>(a.raw) + ((static_cast<int64_t>(b) * a.T + t) * a.H + h) * a.D + a.triv + 4 * v4
                                  : reinterpret_cast<const T*>(a.raw) + b * a.sb + h * a.sh + t * a.st + a.triv + 4 * v4;
-        const float g0 = to_f32<T>(g[0]), g1 = to_f32<T>(g[1]), g2 = to_f32<T>(g[2]), g3 = to_f32<T>(g[3]);
         if (a.part == 0) part += g3 * (M[3] * to_f32<T>(y[0]) + M[7] * to_f32<T>(y[1]) + M[11] * to_f32<T>(y[2]));
         else if (a.part == 3) part += (g0 * M[3] + g1 * M[7] + g2 * M[11]) * to_f32<T>(y[3]) / M[15];
         else part += (g0 * M[3] + g1 * M[7] + g2 * M[11]) * to_f32<T>(y[3]);
@@ -318,39 +340,61 @@ __global__ void gen_dtc_kernel(const GenDtcArgs a) {
 }
 
 struct GenBwdLayout {
-    size_t q, k, v, dout, dq, dk, dv, core, total;
+    size_t q, k, v, dout, dq, dk, dv, oeff, dpad, core, total;
 };
 static GenBwdLayout gen_bwd_layout(const GtaAttnParams& p) {
+    const int Da = padded_dim(p);
     const size_t es = elt(p.in_dtype);
-    const size_t nq = align_up(static_cast<size_t>(p.B) * p.H * p.Tq * p.D * es), nk = align_up(static_cast<size_t>(p.B) * p.H * p.Tk * p.D * es);
+    const size_t nq = align_up(static_cast<size_t>(p.B) * p.H * p.Tq * Da * es), nk = align_up(static_cast<size_t>(p.B) * p.H * p.Tk * Da * es);
     GenBwdLayout l;
     l.q = 0; l.k = l.q + nq; l.v = l.k + nk; l.dout = l.v + nk;
-    l.dq = l.dout + nq; l.dk = l.dq + nq; l.dv = l.dk + nk; l.core = l.dv + nk;
-    l.total = l.core + attn_bwd_workspace_bytes(p.B, p.H, p.Tq, p.Tk, p.D);
+    l.dq = l.dout + nq; l.dk = l.dq + nq; l.dv = l.dk + nk;
+    l.oeff = l.dv + nk;                                   // euclid only: O - tc * translation, padded; dO padded
+    l.dpad = l.oeff + (p.euclid ? nq : 0);
+    l.core = l.dpad + (p.euclid ? nq : 0);
+    l.total = l.core + attn_bwd_workspace_bytes(p.B, p.H, p.Tq, p.Tk, Da);
     return l;
 }
 size_t generic_bwd_workspace_bytes(const GtaAttnParams& p) { return gen_bwd_layout(p).total; }
 
 int launch_attn_bwd_generic(const GtaAttnBwdParams& bp, cudaStream_t st) {
     const GtaAttnParams& p = bp.fwd;
-    if (p.euclid) return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_bwd: euclid_sim has no fused backward");
+    const int Da = padded_dim(p);
+    if (Da > 128) return set_error(GTA_ERR_UNSUPPORTED, "euclid_sim needs head dim + 32 <= 128");
     if (p.out_dtype != p.in_dtype) return set_error(GTA_ERR_UNSUPPORTED, "gta_attn_bwd: out/dout must have the dtype of q/k/v");
     if (!p.lse || !bp.dout || !bp.dq || !bp.dk || !bp.dv) return set_error(GTA_ERR_INVALID, "gta_attn_bwd: null lse/dout/dq/dk/dv");
     const GenBwdLayout l = gen_bwd_layout(p);
     if (!bp.workspace || bp.workspace_bytes < l.total) return set_error(GTA_ERR_INVALID, "gta_attn_bwd: workspace too small (need %zu bytes)", l.total);
     uint8_t* ws = static_cast<uint8_t*>(bp.workspace);
     const bool bf = p.in_dtype == GTA_DTYPE_BF16;
-    for (int which = 0; which < 4; ++which) {          // q', k', v' and dO' = rho_q^{-T} dO (the map applied to q)
+    const int64_t do_sb = static_cast<int64_t>(p.Tq) * p.H * p.D, do_sh = p.D, do_st = static_cast<int64_t>(p.H) * p.D;   // [B,Tq,H,D] as [B,H,T,D]
+    for (int which = 0; which < 4; ++which) {          // q', k', v' as in the forward, and dO' = (output map)^T dO
         GenArgs a = make_gen_args(p, which == 3 ? 0 : which);
-        a.ones = 0;
         if (which == 3) {
-            a.x = bp.dout;
-            a.sb = static_cast<int64_t>(p.Tq) * p.H * p.D; a.sh = p.D; a.st = static_cast<int64_t>(p.H) * p.D;
+            a.x = bp.dout; a.sb = do_sb; a.sh = do_sh; a.st = do_st;
             a.rotate = p.v_transform;
             a.out_bthd = 1;
+            a.ones = 0;
+            if (p.euclid) { a.se3m = p.reps.se3_q; a.se3_lin_t = 1; }      // output: y = A_o x + t_o tc with A_o | t_o from E_q (gta.py:251-253)
         }
         a.out = ws + (which == 0 ? l.q : (which == 1 ? l.k : (which == 2 ? l.v : l.dout)));
         if (bf) launch_in<__nv_bfloat16, __nv_bfloat16>(a, st); else launch_in<float, float>(a, st);
+    }
+    if (p.euclid) {
+        const int64_t rows = static_cast<int64_t>(p.B) * p.H * p.Tk;
+        const unsigned blocks = static_cast<unsigned>((rows + 127) / 128);
+        if (bf) gen_key_bias_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(ws + l.k), rows, p.D, Da);
+        else gen_key_bias_kernel<float><<<blocks, 128, 0, st>>>(reinterpret_cast<float*>(ws + l.k), rows, p.D, Da);
+        // delta = rowsum(dO' * O') with O = A_o O' + t_o tc: rowsum(dO * (O - t_o tc)) -> the pair (O - t_o tc, dO), padded to Da
+        for (int which = 0; which < 2; ++which) {
+            GenArgs a = make_gen_args(p, 0);
+            a.x = which == 0 ? p.out : bp.dout; a.sb = do_sb; a.sh = do_sh; a.st = do_st;
+            a.ones = 0; a.out_bthd = 1;
+            a.rotate = which == 0 && p.v_transform;
+            a.se3m = p.reps.se3_q; a.sub_trans = 1;
+            a.out = ws + (which == 0 ? l.oeff : l.dpad);
+            if (bf) launch_in<__nv_bfloat16, __nv_bfloat16>(a, st); else launch_in<float, float>(a, st);
+        }
     }
     int rc = check_launch("gta_attn_bwd (generic rep application)");
     if (rc) return rc;
@@ -358,19 +402,20 @@ int launch_attn_bwd_generic(const GtaAttnBwdParams& bp, cudaStream_t st) {
     GtaAttnBwdParams c = bp;                           // the tensor-core backward on the prepared operands
     GtaAttnParams& f = c.fwd;
     f.q = ws + l.q; f.k = ws + l.k; f.v = ws + l.v;
-    f.q_stride_t = f.k_stride_t = f.v_stride_t = p.D;
-    f.q_stride_h = static_cast<int64_t>(p.Tq) * p.D; f.k_stride_h = f.v_stride_h = static_cast<int64_t>(p.Tk) * p.D;
+    f.q_stride_t = f.k_stride_t = f.v_stride_t = Da;
+    f.q_stride_h = static_cast<int64_t>(p.Tq) * Da; f.k_stride_h = f.v_stride_h = static_cast<int64_t>(p.Tk) * Da;
     f.q_stride_b = f.q_stride_h * p.H; f.k_stride_b = f.v_stride_b = f.k_stride_h * p.H;
-    f.triv = p.D; f.se3 = f.so3 = f.so2 = f.t2 = 0; f.euclid = 0;
+    f.D = Da; f.triv = Da; f.se3 = f.so3 = f.so2 = f.t2 = 0; f.euclid = 0;
     f.reps = GtaReps{};
     f.trans_coeff = nullptr;
     f.v_transform = 0;
+    if (p.euclid) f.out = ws + l.oeff;
     c.dout = ws + l.dout;
     c.dq = ws + l.dq; c.dk = ws + l.dk; c.dv = ws + l.dv;
     c.dtrans_coeff = nullptr;
     c.workspace = ws + l.core;
     c.workspace_bytes = bp.workspace_bytes - l.core;
-    rc = launch_attn_bwd(c, st, /*delta_dout=*/bp.dout);   // delta from the un-rotated (O, dO) pair
+    rc = launch_attn_bwd(c, st, /*delta_dout=*/p.euclid ? static_cast<const void*>(ws + l.dpad) : bp.dout);   // delta from the un-rotated pair
     if (rc) return rc;
 
     if (bp.dtrans_coeff && p.se3 > 0) {
@@ -383,22 +428,30 @@ int launch_attn_bwd_generic(const GtaAttnBwdParams& bp, cudaStream_t st) {
             d.sh = part == 0 ? p.q_stride_h : (part == 1 ? p.k_stride_h : p.v_stride_h);
             d.st = part == 0 ? p.q_stride_t : (part == 1 ? p.k_stride_t : p.v_stride_t);
             d.g = part == 0 ? static_cast<const void*>(ws + l.dq) : (part == 1 ? ws + l.dk : (part == 2 ? ws + l.dv : bp.dout));
-            d.se3m = qside ? p.reps.se3_q : p.reps.se3_k;
+            d.Dg = part == 3 ? p.D : Da;
+            // euclid: the query side uses c_q = inv(E_q) (se3_qi), the output side E_q (gta.py:140,153,251-253)
+            d.se3m = qside ? ((p.euclid && part == 0) ? p.reps.se3_qi : p.reps.se3_q) : p.reps.se3_k;
             d.dtc = bp.dtrans_coeff;
             d.B = p.B; d.H = p.H; d.D = p.D; d.T = qside ? p.Tq : p.Tk; d.N = qside ? p.Nq : p.Nk; d.tpv = d.T / d.N;
-            d.triv = p.triv; d.se3 = p.se3; d.part = part;
-            const int64_t total = static_cast<int64_t>(d.B) * d.T * d.H * (d.se3 >> 2);
+            d.triv = p.triv; d.se3 = p.se3; d.part = part; d.euclid = p.euclid;
+            d.bias_k = (p.euclid && part == 1) ? ws + l.k : nullptr; d.Da = Da;
+            const int64_t total = static_cast<int64_t>(d.B) * d.T * d.H * (d.se3 / (p.euclid ? 3 : 4));
             const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 148 * 8));
             if (bf) gen_dtc_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(d); else gen_dtc_kernel<float><<<blocks, 256, 0, st>>>(d);
         }
     }
-    for (int which = 0; which < 3; ++which) {          // dq = rho_q^{-1} dQ', dk = rho_k^T dK', dv = rho_k^T dV'
+    for (int which = 0; which < 3; ++which) {          // dq = (query map)^T dQ', dk = rho_k^T dK', dv = rho_k^T dV'
         GenArgs o = make_gen_args(p, which == 0 ? 3 : which);
         if (which > 0) o.mode = kModeKVT;
-        o.Da = p.D;
+        o.ones = 0;
         o.x = ws + (which == 0 ? l.dq : (which == 1 ? l.dk : l.dv));
         o.out = which == 0 ? bp.dq : (which == 1 ? bp.dk : bp.dv);
         o.rotate = (which < 2) || p.v_transform;
+        if (p.euclid) {
+            o.se3_lin_t = 1;
+            if (which == 0) o.se3m = p.reps.se3_qi;     // q' = A_q q + t_q tc with A_q | t_q from inv(E_q)
+            if (which == 1) o.bias_k = ws + l.k;        // the -|k'|^2/2 columns: dk' = g[:D] - g[D] k'
+        }
         const int64_t total = static_cast<int64_t>(o.B) * o.T * o.H * o.D;
         const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
         if (bf) gen_rotate_out_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>(o);

@@ -8,8 +8,11 @@
 
 namespace gta {
 
+#ifndef GTA_ROT_MINB
+#define GTA_ROT_MINB 1
+#endif
 template <typename T, bool kQSide>
-__global__ void __launch_bounds__(128) rotate_kv_kernel(const RotArgs a) {
+__global__ void __launch_bounds__(128, GTA_ROT_MINB) rotate_kv_kernel(const RotArgs a) {
     const float tc = a.tc_ptr ? __ldg(a.tc_ptr) : 1.0f;
     rotate_tile<T, kQSide>(a, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x >> 5, threadIdx.x & 31, tc);
 }

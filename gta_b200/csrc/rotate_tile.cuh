@@ -33,7 +33,10 @@ __device__ __forceinline__ void split_chunk_bf16(const float* x, uint4& hi, uint
 // so3, then so2) so that every instruction is type-uniform while lanes still cover contiguous 16-byte chunks.
 // K and V of the same (key, chunk) share the rep data, and kUnroll (key, chunk) items are loaded before the first
 // one is consumed: ~2*kUnroll 16-byte loads in flight per thread keep HBM busy at low occupancy cost.
-constexpr int kRotUnroll = 3;
+#ifndef GTA_ROT_UNROLL
+#define GTA_ROT_UNROLL 3
+#endif
+constexpr int kRotUnroll = GTA_ROT_UNROLL;
 
 // kQSide = false: K' = rho_k K, V' = rho_k V (forward and backward staging).
 // kQSide = true : the same walk applied to the QUERY side of the backward: Q' = rho_q^{-T} Q and dO' = rho_q^{-T} dO share

@@ -227,12 +227,12 @@ class _FusedGtaAttention(torch.autograd.Function):
     reference (SO(3) reps are detached at gta.py:194-197, the SE(3) / SO(2) / coordinates come from the batch)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, trans_coeff, packed, f_dims, scale, v_transform, flags):
+    def forward(ctx, q, k, v, trans_coeff, packed, f_dims, scale, v_transform, flags, euclid=False):
         tc = None if trans_coeff is None else trans_coeff.detach()
         out, lse = ops.gta_attention_fwd(q, k, v, packed, f_dims, trans_coeff=tc, scale=scale, v_transform=v_transform,
-                                         return_lse=True, flags=flags)
+                                         return_lse=True, flags=flags, euclid=euclid)
         ctx.save_for_backward(q, k, v, out, lse, tc if tc is not None else q.new_empty(0))
-        ctx.packed, ctx.f_dims, ctx.scale, ctx.v_transform = packed, f_dims, scale, v_transform
+        ctx.packed, ctx.f_dims, ctx.scale, ctx.v_transform, ctx.euclid = packed, f_dims, scale, v_transform, euclid
         ctx.has_tc = tc is not None
         ctx.tc_shape = None if trans_coeff is None else trans_coeff.shape
         return out
@@ -242,11 +242,11 @@ class _FusedGtaAttention(torch.autograd.Function):
         q, k, v, out, lse, tc = ctx.saved_tensors
         dq, dk, dv, dtc = ops.gta_attention_bwd(dout, q, k, v, out, lse, ctx.packed, ctx.f_dims,
                                                 trans_coeff=tc if ctx.has_tc else None, scale=ctx.scale,
-                                                v_transform=ctx.v_transform)
+                                                v_transform=ctx.v_transform, euclid=ctx.euclid)
         gtc = None
         if ctx.has_tc and ctx.needs_input_grad[3] and dtc is not None:
             gtc = dtc.reshape(ctx.tc_shape).to(tc.dtype)
-        return dq, dk, dv, gtc, None, None, None, None, None
+        return dq, dk, dv, gtc, None, None, None, None, None, None
 
 
 def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, trans_coeff=1.0, v_transform=True,
@@ -264,8 +264,6 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
     grad_on = torch.is_grad_enabled()
     needs_grad = grad_on and (any(t.requires_grad for t in (q, k, v)) or
                               (torch.is_tensor(trans_coeff) and trans_coeff.requires_grad))
-    if needs_grad and euclid:
-        return deleg("autograd through euclid_sim (its forward has no log-sum-exp output)")
     if g("so3") and not g("se3"):
         return deleg("so3 without se3 (undefined in the reference as well, SURVEY T5)")
     # softmax temperature: a closure variable of attn_fn.forward, never a keyword of this function
@@ -301,7 +299,7 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
                        "(1e-2 budget, as under bf16 autocast); set GTA_B200_FP32_TRAIN=reference to train through the "
                        "reference function instead")
             flags = ops.FLAG_FAST_FP32
-        out = _FusedGtaAttention.apply(q, k, v, tc, packed, dict(f_dims), scale, bool(v_transform), flags)
+        out = _FusedGtaAttention.apply(q, k, v, tc, packed, dict(f_dims), scale, bool(v_transform), flags, bool(euclid))
         attn = None
         if want_map:
             with torch.no_grad():

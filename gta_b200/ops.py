@@ -174,7 +174,7 @@ def gta_attention_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, reps: P
 def gta_attention_bwd(dout: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor,
                       lse: torch.Tensor, reps: PackedReps, f_dims: dict, *, trans_coeff: Optional[torch.Tensor] = None,
                       scale: Optional[float] = None, v_transform: bool = True,
-                      debug_clocks: Optional[torch.Tensor] = None, flags: int = 0):
+                      debug_clocks: Optional[torch.Tensor] = None, flags: int = 0, euclid: bool = False):
     """Backward of gta_attention_fwd.  `out` is the forward result ([B,H,Tq,D] view of a [B,Tq,H,D] buffer), `lse` its
     log-sum-exp, `dout` the gradient w.r.t. `out` (any layout).  Returns (dq, dk, dv, dtrans_coeff) with dq/dk/dv shaped
     like q/k/v (views of contiguous [B,T,H,D] buffers) and dtrans_coeff a [1] fp32 tensor (None without an se3 block)."""
@@ -193,7 +193,7 @@ def gta_attention_bwd(dout: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: t
     has_se3 = bool(int(f_dims.get("se3", 0) or 0))
     dtc = torch.zeros(1, device=dev, dtype=torch.float32) if has_se3 else None
     bp = GtaAttnBwdParams()
-    bp.fwd = _params(q, k, v, o_c, reps, f_dims, trans_coeff, scale, v_transform, flags, lse.contiguous())
+    bp.fwd = _params(q, k, v, o_c, reps, f_dims, trans_coeff, scale, v_transform, flags, lse.contiguous(), euclid)
     bp.fwd.debug_clocks = _ptr(debug_clocks)
     bp.dout, bp.dq, bp.dk, bp.dv, bp.dtrans_coeff = _ptr(do_c), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dtc)
     nbytes = lib().gta_attn_bwd_workspace_bytes_p(ctypes.byref(bp.fwd))     # (covers the generic-path layouts: t2, unaligned blocks)

@@ -75,9 +75,12 @@ def test_backward_and_probs_argument_validation():
     # generic-path layouts (t2 block / unaligned blocks) have a backward of their own; it validates its arguments first
     assert l.gta_attn_bwd(ctypes.byref(bp), None) == -1 and "lse" in l.gta_last_error().decode()
     assert l.gta_attn_bwd_workspace_bytes_p(ctypes.byref(bp.fwd)) == 7 * 2048 + l.gta_attn_bwd_workspace_bytes(1, 2, 16, 16, 32)
-    bp.fwd.euclid = 1
-    bp.fwd.reps.se3_qi = 0x1000
-    assert l.gta_attn_bwd(ctypes.byref(bp), None) == -3 and "euclid_sim" in l.gta_last_error().decode()
+    eu = _params(se3=15, so3=8, so2=0, euclid=1, D=96, triv=73)          # euclid_sim (padded head dim 128): served as well
+    eu.reps = _lib.GtaReps(*([0x1000] * 7), None, None)
+    bp.fwd = eu
+    assert l.gta_attn_bwd(ctypes.byref(bp), None) == -1 and "lse" in l.gta_last_error().decode()
+    dense = lambda T: (2 * T * 128 * 2 + 1023) // 1024 * 1024
+    assert l.gta_attn_bwd_workspace_bytes_p(ctypes.byref(eu)) == 9 * dense(16) + l.gta_attn_bwd_workspace_bytes(1, 2, 16, 16, 128)
     assert l.gta_attn_bwd(None, None) == -1
     # Q' and dO' images, K' | V' images, delta, and (head dims <= 96: the fused kernel) the fp32 dQ' accumulation tiles
     assert l.gta_attn_bwd_workspace_bytes(1, 2, 16, 16, 32) == 2 * 2 * 8192 + 2 * 2 * 8192 + 1024 + 2 * 128 * 32 * 4

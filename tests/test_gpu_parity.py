@@ -491,7 +491,10 @@ def _grad_oracle(cfg, inp, tc, dout):
         if t.requires_grad and not t.is_leaf:
             t.retain_grad()
     # the tail of tp.gta_attention on these very tensors (so that qt/kt/vt.grad are populated)
-    out = torch.softmax(qt @ kt.transpose(-1, -2) * cfg.head_dim ** -0.5, -1) @ vt
+    sim = qt @ kt.transpose(-1, -2)
+    if cfg.euclid:                          # EuclidAttnFn, layers.py:219-223
+        sim = sim - 0.5 * qt.pow(2).sum(-1)[..., None] - 0.5 * kt.pow(2).sum(-1)[..., None, :]
+    out = torch.softmax(sim * cfg.head_dim ** -0.5, -1) @ vt
     if cfg.v_transform:
         has = lambda n: reps[n].transpose(-1, -2) if n in reps else None
         Ao = tp._scale_translation(reps["se3_qinv"], tcv) if cfg.dims()[1] else None
@@ -504,16 +507,23 @@ def _grad_oracle(cfg, inp, tc, dout):
     tc_scale = 0.0
     if se3:
         B, H = q.shape[:2]
-        v4 = lambda x, N: x.detach()[..., triv:triv + se3].reshape(B, H, N, -1, se3 // 4, 4)
+        n = 3 if cfg.euclid else 4
+        v4 = lambda x, N: x.detach()[..., triv:triv + se3].reshape(B, H, N, -1, se3 // n, n)
         col = lambda g, M: g[..., 0] * M[..., 0, 3] + g[..., 1] * M[..., 1, 3] + g[..., 2] * M[..., 2, 3]
         Eq, Ek = reps["se3_qinv"][:, None, :, None, None], reps["se3_k"][:, None, :, None, None]
         Nq, Nk = cfg.n_q_views, cfg.n_k_views
-        Q4 = v4(q, Nq)
-        parts = [(v4(qt.grad, Nq)[..., 3] * (Eq[..., 0, 3] * Q4[..., 0] + Eq[..., 1, 3] * Q4[..., 1] + Eq[..., 2, 3] * Q4[..., 2])).sum(),
-                 (col(v4(kt.grad, Nk), Ek) * v4(k, Nk)[..., 3]).sum()]
-        if cfg.v_transform:
-            parts += [(col(v4(vt.grad, Nk), Ek) * v4(v, Nk)[..., 3]).sum(),
-                      (col(v4(dout.double(), Nq), Eq) * v4(out, Nq)[..., 3] / Eq[..., 3, 3]).sum()]
+        if cfg.euclid:      # y = A x + t tc for every side (homogenised 3-vectors): d/dtc = gradient . translation column
+            Cq = reps["se3_q"][:, None, :, None, None]
+            parts = [col(v4(qt.grad, Nq), Cq).sum(), col(v4(kt.grad, Nk), Ek).sum()]
+            if cfg.v_transform:
+                parts += [col(v4(vt.grad, Nk), Ek).sum(), col(v4(dout.double(), Nq), Eq).sum()]
+        else:
+            Q4 = v4(q, Nq)
+            parts = [(v4(qt.grad, Nq)[..., 3] * (Eq[..., 0, 3] * Q4[..., 0] + Eq[..., 1, 3] * Q4[..., 1] + Eq[..., 2, 3] * Q4[..., 2])).sum(),
+                     (col(v4(kt.grad, Nk), Ek) * v4(k, Nk)[..., 3]).sum()]
+            if cfg.v_transform:
+                parts += [(col(v4(vt.grad, Nk), Ek) * v4(v, Nk)[..., 3]).sum(),
+                          (col(v4(dout.double(), Nq), Eq) * v4(out, Nq)[..., 3] / Eq[..., 3, 3]).sum()]
         assert abs(float(sum(parts)) - float(tcv.grad)) < 1e-6 * max(1.0, float(sum(p.abs() for p in parts)))
         tc_scale = float(sum(p.abs() for p in parts))
     g = lambda t: None if t is None else t.float().numpy()
@@ -532,8 +542,11 @@ def _grad_oracle(cfg, inp, tc, dout):
     (CLEVR_T2, 3, 2, 171, 300, True, 1, torch.bfloat16, 0.3, True),     # generic path: triv 2 | se3 32 | t2 30 (runs/clevrtr/GTA/gta_t2)
     (MSN_T2, 2, 2, 100, 100, False, 2, torch.bfloat16, 0.3, True),      # generic path: se3 48 | t2 48 (runs/msn/GTA/gta_t2)
     (CLEVR_T2, 2, 2, 150, 150, False, 1, torch.float32, 0.5, False),    # generic path, fp32 I/O, v_transform = False
+    (CLEVR_EUCLID, 3, 2, 171, 300, True, 1, torch.bfloat16, 0.3, True), # euclid_sim: triv 2 | se3 30 | so2 32 (runs/clevrtr/GTA/gta_euclid), padded head dim 96
+    (MSN_SO3_EUCLID, 2, 2, 100, 100, False, 2, torch.bfloat16, 0.3, True),  # euclid_sim + so3, padded head dim 128 (kernel pair)
+    (CLEVR_EUCLID, 2, 2, 150, 150, False, 1, torch.bfloat16, 0.5, False),   # euclid_sim, v_transform = False
 ], ids=["cfg1b", "msn_cross", "msn_enc", "clevr_dec", "clevr_novt", "msn_cross_f32", "clevr_dec_full", "msn_dec_full",
-        "clevr_t2_cross", "msn_t2", "clevr_t2_f32_novt"])
+        "clevr_t2_cross", "msn_t2", "clevr_t2_f32_novt", "clevr_euclid_cross", "msn_so3_euclid", "clevr_euclid_novt"])
 def test_fused_backward_matches_autograd_oracle(case):
     """dq, dk, dv and d(trans_coeff) of the fused backward, through the public drop-in under autograd, against fp64
     autograd of the oracle on the same (rounded) inputs.  bf16 tensor-core math: errors relative to the gradient scale."""
@@ -562,11 +575,12 @@ def test_fused_backward_matches_autograd_oracle(case):
     q, k, v = (inp[n].cuda().clone().requires_grad_(True) for n in "qkv")
     tcp = torch.nn.Parameter(torch.tensor([tc], device="cuda"))
     out, _ = fast.multihead_geometric_transform_attention(q, k, v, AttnFn(), cfg.f_dims, extras, trans_coeff=tcp,
-                                                          v_transform=vt)
+                                                          v_transform=vt, euclid=cfg.euclid)
     assert out.requires_grad
     out.backward(dout.cuda())
     torch.cuda.synchronize()
-    _check(out.detach().float().cpu().numpy(), ref_out, tc, BF16_TOL, "forward under autograd")
+    # (euclid_sim in bf16 math: logits carry -|k'|^2/2 terms of tens of units, bound relative as in the forward tests)
+    _check(out.detach().float().cpu().numpy(), ref_out, tc, BF16_TOL, "forward under autograd", rel=cfg.euclid)
     for name, got, ref in (("dq", q.grad, rq), ("dk", k.grad, rk), ("dv", v.grad, rv)):
         got = got.float().cpu().numpy()
         assert np.isfinite(got).all(), name

@@ -181,7 +181,9 @@ def test_ablation_blocks_against_live_reference(base, nq, nk, tq, tk, cross, vt)
 
 
 @pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted (GPU box)")
-@pytest.mark.parametrize("base,nq,nk,tq,tk,cross", [(MSN_SO3, 3, 2, 8, 16, True), (CLEVR, 2, 2, 21, 21, False)])
+@pytest.mark.parametrize("base,nq,nk,tq,tk,cross", [(MSN_SO3, 3, 2, 8, 16, True), (CLEVR, 2, 2, 21, 21, False),
+                                                    (CLEVR_T2, 2, 2, 21, 21, False), (CLEVR_EUCLID, 3, 2, 8, 16, True),
+                                                    (MSN_SO3_EUCLID, 2, 2, 9, 9, False)])
 def test_grad_oracle_matches_reference_autograd(base, nq, nk, tq, tk, cross):
     """The gradient checker of the GPU tests (autograd through oracle/torch_port.py) against autograd through the
     UNMODIFIED reference function: dq, dk, dv and d(trans_coeff)."""
@@ -196,8 +198,8 @@ def test_grad_oracle_matches_reference_autograd(base, nq, nk, tq, tk, cross):
             m = ref_harness.load()
             extras = ref_harness.ref_reps(cfg, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"], cross)
             out, _ = m.gta.multihead_geometric_transform_attention(
-                q, k, v, attn_fn=ref_harness._AttnFn(cfg.head_dim ** -0.5), f_dims=dict(cfg.f_dims), reps=extras,
-                trans_coeff=tc, v_transform=True, euclid=False)
+                q, k, v, attn_fn=ref_harness._AttnFn(cfg.head_dim ** -0.5, euclid=cfg.euclid), f_dims=dict(cfg.f_dims), reps=extras,
+                trans_coeff=tc, v_transform=True, euclid=cfg.euclid)
         else:
             out = tp.gta_attention(cfg, q, k, v, inp["extr_q"], inp["extr_k"], inp["coord_q"], inp["coord_k"], trans_coeff=tc)
         out.backward(dout)
