@@ -227,7 +227,9 @@ class _FusedGtaAttention(torch.autograd.Function):
     reference (SO(3) reps are detached at gta.py:194-197, the SE(3) / SO(2) / coordinates come from the batch)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, trans_coeff, packed, f_dims, scale, v_transform, flags, euclid=False):
+    def forward(ctx, q, k, v, trans_coeff, packed, f_dims, scale, v_transform, flags, euclid=False, tau=None):
+        # tau: the learnable softmax temperature (layers.py:195-200) when it needs a gradient; `scale` already holds 1 / tau
+        ctx.tau = tau
         tc = None if trans_coeff is None else trans_coeff.detach()
         out, lse = ops.gta_attention_fwd(q, k, v, packed, f_dims, trans_coeff=tc, scale=scale, v_transform=v_transform,
                                          return_lse=True, flags=flags, euclid=euclid)
@@ -246,7 +248,12 @@ class _FusedGtaAttention(torch.autograd.Function):
         gtc = None
         if ctx.has_tc and ctx.needs_input_grad[3] and dtc is not None:
             gtc = dtc.reshape(ctx.tc_shape).to(tc.dtype)
-        return dq, dk, dv, gtc, None, None, None, None, None, None
+        gtau = None
+        if ctx.tau is not None and ctx.needs_input_grad[10]:
+            # logits L = scale0 (q'.k') / tau  =>  dL/dtau = -L / tau, and sum_j G_ij L_ij = q'_i . dq'_i = q_i . dq_i (the reps
+            # are linear maps: q . J^T g = (J q) . g), so d(loss)/d(tau) = -(1 / tau) sum(q * dq): one reduction, no extra kernel
+            gtau = (-(q.float() * dq.float()).sum() / ctx.tau.detach().float().reshape(-1)[0]).reshape(ctx.tau.shape).to(ctx.tau.dtype)
+        return dq, dk, dv, gtc, None, None, None, None, None, None, gtau
 
 
 def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, trans_coeff=1.0, v_transform=True,
@@ -270,10 +277,14 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
     tau, _ = _closure_tau(attn_fn)
     if "tau" in kwargs:
         tau = kwargs["tau"]
+    tau_param = None
     if torch.is_tensor(tau):
         if grad_on and tau.requires_grad:
-            return deleg("a learnable softmax temperature that needs a gradient (softmax: adjustable)")
-        tau = float(tau.detach().reshape(-1)[0])           # host read of a scalar parameter (evaluation only)
+            if euclid:      # the |q'|^2, |k'|^2 terms of EuclidAttnFn are divided by tau as well: not covered by the q . dq identity
+                return deleg("a learnable softmax temperature that needs a gradient, with euclid_sim")
+            tau_param = tau
+        tau = float(tau.detach().reshape(-1)[0])           # host read of a scalar parameter
+    needs_grad = needs_grad or tau_param is not None
     if needs_grad and q.dtype == torch.float32 and FP32_TRAINING == "reference":
         return deleg("fp32 training (GTA_B200_FP32_TRAIN=reference)")
     B, H, Tq, D = q.shape
@@ -299,7 +310,7 @@ def multihead_geometric_transform_attention(q, k, v, attn_fn, f_dims, reps, tran
                        "(1e-2 budget, as under bf16 autocast); set GTA_B200_FP32_TRAIN=reference to train through the "
                        "reference function instead")
             flags = ops.FLAG_FAST_FP32
-        out = _FusedGtaAttention.apply(q, k, v, tc, packed, dict(f_dims), scale, bool(v_transform), flags, bool(euclid))
+        out = _FusedGtaAttention.apply(q, k, v, tc, packed, dict(f_dims), scale, bool(v_transform), flags, bool(euclid), tau_param)
         attn = None
         if want_map:
             with torch.no_grad():
