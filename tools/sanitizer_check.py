@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from gta_b200 import _lib, ops  # noqa: E402
-from gta_b200.synth import CFG1_A, CLEVR, MSN_SO3, GtaConfig, make_inputs  # noqa: E402
+from gta_b200.synth import CFG1_A, CLEVR, CLEVR_EUCLID, CLEVR_T2, MSN_SO3, MSN_SO3_EUCLID, GtaConfig, make_inputs  # noqa: E402
 
 CASES = [("cfg1", CFG1_A, 2, 2, 256, 256, False), ("clevr_enc", CLEVR, 2, 2, 300, 300, False),
          ("clevr_dec", CLEVR, 3, 2, 171, 300, True), ("msn_small", MSN_SO3, 5, 5, 64, 64, False)]
@@ -42,3 +42,20 @@ for name, base, nq, nk, tq, tk, cross in CASES:
             g = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=bfl)
             torch.cuda.synchronize()
             print("%-10s backward ok (%s), |dq|max %.3f" % (name, bname, float(g[0].float().abs().max())), flush=True)
+
+# generic-path layouts (t2 block, euclid_sim): forward + backward through the element-wise rep passes
+if not only or "generic" in only:
+    for name, base, nq, nk, tq, tk, cross in [("clevr_t2", CLEVR_T2, 3, 2, 57, 100, True), ("clevr_euclid", CLEVR_EUCLID, 2, 2, 75, 75, False),
+                                              ("msn_so3_euclid", MSN_SO3_EUCLID, 2, 2, 40, 40, False)]:
+        cfg = GtaConfig(**base, n_q_views=nq, n_k_views=nk)
+        inp = make_inputs(cfg, 1, tq, tk, cross=cross, seed=5, dtype=torch.bfloat16)
+        ek, ck = inp["extr_k"].cuda(), inp["coord_k"].cuda()
+        eq = inp["extr_q"].cuda() if cross else ek
+        cq = inp["coord_q"].cuda() if cross else ck
+        reps = ops.build_reps(eq, ek, cq, ck, so2_nfreqs=cfg.so2, so3_maxdeg=cfg.so3, t2=bool(cfg.t2_dim()), euclid=cfg.euclid)
+        q, k, v = (inp[n].cuda() for n in "qkv")
+        tc = torch.tensor([0.3], device="cuda")
+        out, lse = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True, euclid=cfg.euclid)
+        g = ops.gta_attention_bwd(torch.randn_like(out), q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, euclid=cfg.euclid)
+        torch.cuda.synchronize()
+        print("%-14s generic forward + backward ok, |dq|max %.3f d(tc) %.4f" % (name, float(g[0].float().abs().max()), float(g[3])), flush=True)
