@@ -606,7 +606,11 @@ int launch_attn_bwd(const GtaAttnBwdParams& bp, cudaStream_t st, const void* del
     a.dq_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(delta) + bwd_align(static_cast<size_t>(p.B) * p.H * p.Tq * 4));
     // head dims <= 96: ONE kernel for dK, dV and the dQ' partial sums (gta_attn_bwd2.cu); GTA_FLAG_BWD_SPLIT keeps the
     // dK/dV + dQ kernel pair (the only path for head dim 128)
-    if (bwd_fused_supported(p.D) && !(p.flags & GTA_FLAG_BWD_SPLIT)) return launch_bwd_fused(a, bf, p.D, (p.flags & GTA_FLAG_RUNTIME_LAYOUT) != 0, st);
+    // (calls of less than one wave of key tiles are launch-bound: the pair's two launches beat memset + fused + finishing
+    // kernel by ~6 % at BASELINE config 1; GTA_FLAG_SINGLE_LAUNCH forces the fused kernel there too)
+    const bool tiny = static_cast<int64_t>(p.B) * p.H * ntk < 148 && !(p.flags & GTA_FLAG_SINGLE_LAUNCH);
+    if (bwd_fused_supported(p.D) && !(p.flags & GTA_FLAG_BWD_SPLIT) && !tiny)
+        return launch_bwd_fused(a, bf, p.D, (p.flags & GTA_FLAG_RUNTIME_LAYOUT) != 0, st);
     return bf ? launch_bwd_t<__nv_bfloat16>(a, p.D, st) : launch_bwd_t<float>(a, p.D, st);
 }
 

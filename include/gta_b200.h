@@ -115,7 +115,8 @@ typedef struct GtaAttnParams {
 #define GTA_FLAG_RUNTIME_LAYOUT 2048 /* single-launch kernel: use the run-time-layout staging code even for a layout that has a
                                        compile-time-specialised instantiation (A/B measurement, tests) */
 #define GTA_FLAG_BWD_SPLIT 4096 /* gta_attn_bwd: keep the dK/dV kernel + dQ kernel pair (S and dP computed twice) instead of the fused
-                                  * kernel that accumulates the dQ partial sums with bulk reductions (head dims <= 96) */
+                                  * kernel that accumulates the dQ partial sums with bulk reductions (head dims <= 96; calls of fewer than 148 key tiles
+                                  * use the pair by default, GTA_FLAG_SINGLE_LAUNCH forces the fused kernel) */
 #define GTA_FLAG_V3_PRESTAGED 64 /* with GTA_FLAG_SKIP_STAGE: run the single-launch kernel on an already staged workspace
                                    (its rotation warps idle) instead of the two-launch attention kernel */
 

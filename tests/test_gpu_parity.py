@@ -612,7 +612,8 @@ def test_backward_abi_direct_and_linearity():
 @pytest.mark.parametrize("case", [
     (CFG1_B, 2, 2, 16, 16, False, 2), (MSN_SO3, 3, 2, 40, 64, True, 2), (MSN_SO3, 5, 5, 256, 256, False, 1),
     (CLEVR, 3, 2, 171, 300, True, 1), (CLEVR, 3, 2, 853, 300, True, 1), (MSN_SO3, 2, 5, 256, 256, True, 1),
-], ids=["cfg1b", "msn_cross", "msn_enc", "clevr_dec", "clevr_dec_full", "msn_more_keys"])
+    (CLEVR_T2, 3, 2, 171, 300, True, 1), (CLEVR_EUCLID, 2, 2, 150, 150, False, 1),     # generic path around both cores
+], ids=["cfg1b", "msn_cross", "msn_enc", "clevr_dec", "clevr_dec_full", "msn_more_keys", "clevr_t2", "clevr_euclid"])
 def test_backward_fused_kernel_matches_kernel_pair(case):
     """The fused backward kernel (dK, dV and bulk-reduced dQ partial sums in one launch; default for head dims <= 96) against
     the dK/dV + dQ kernel pair (GTA_FLAG_BWD_SPLIT) on the same call: same bf16 operands, different summation order."""
@@ -624,13 +625,15 @@ def test_backward_fused_kernel_matches_kernel_pair(case):
     reps = _dev_reps(cfg, inp)
     q, k, v = (inp[n].cuda() for n in "qkv")
     tc = torch.tensor([0.3], device="cuda")
-    out, lse = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True)
+    eu = dict(euclid=cfg.euclid)
+    out, lse = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True, **eu)
     dout = torch.randn(out.shape, device="cuda").bfloat16()
-    fused = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc)
-    again = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc)
-    pair = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=_lib.GTA_FLAG_BWD_SPLIT)
+    force = _lib.GTA_FLAG_SINGLE_LAUNCH      # (calls of less than one wave of key tiles default to the kernel pair)
+    fused = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=force, **eu)
+    again = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=force, **eu)
+    pair = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=_lib.GTA_FLAG_BWD_SPLIT, **eu)
     # the run-time-layout epilogue (head layouts without a compile-time instantiation) on the same call
-    rt = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=_lib.GTA_FLAG_RUNTIME_LAYOUT)
+    rt = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=force | _lib.GTA_FLAG_RUNTIME_LAYOUT, **eu)
     torch.cuda.synchronize()
     for name, a, b in zip(("dq", "dk", "dv"), fused[:3], rt[:3]):
         if name == "dq":

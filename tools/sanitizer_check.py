@@ -38,7 +38,7 @@ for name, base, nq, nk, tq, tk, cross in CASES:
     if not only or "backward" in only:
         out, lse = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True)
         dout = torch.randn_like(out)
-        for bname, bfl in (("fused kernel", 0), ("fused kernel, run-time layout", _lib.GTA_FLAG_RUNTIME_LAYOUT), ("kernel pair", _lib.GTA_FLAG_BWD_SPLIT)):
+        for bname, bfl in (("fused kernel", _lib.GTA_FLAG_SINGLE_LAUNCH), ("fused kernel, run-time layout", _lib.GTA_FLAG_SINGLE_LAUNCH | _lib.GTA_FLAG_RUNTIME_LAYOUT), ("kernel pair", _lib.GTA_FLAG_BWD_SPLIT)):
             g = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=bfl)
             torch.cuda.synchronize()
             print("%-10s backward ok (%s), |dq|max %.3f" % (name, bname, float(g[0].float().abs().max())), flush=True)
