@@ -654,6 +654,51 @@ def test_backward_fused_kernel_matches_kernel_pair(case):
         assert abs(float(fused[3]) - float(pair[3])) <= 1e-2 * max(1.0, abs(float(pair[3])))
 
 
+def test_backward_headline_batch_and_long_sequence():
+    """The backward at benchmark sizes through size-independent properties: (i) MSN encoder shape at B = 64 (5 120 CTAs of the
+    fused kernel): the gradients of a batch element do not depend on the rest of the batch — three elements are recomputed at
+    B = 1 (dK / dV bit-equal, dQ up to the order of its fp32 partial sums); (ii) L = 8 192 (64 query tiles per key tile: ring
+    slots and barrier parities over many pairs): fused kernel against the kernel pair."""
+    from gta_b200 import _lib
+    ops = _ops()
+    cfg = GtaConfig(**MSN_SO3, n_q_views=5, n_k_views=5)
+    B = 64
+    inp = make_inputs(cfg, B, 256, 256, cross=False, seed=71, dtype=torch.bfloat16)
+    reps = _dev_reps(cfg, inp)
+    q, k, v = (inp[n].cuda() for n in "qkv")
+    tc = torch.tensor([0.01], device="cuda")
+    out, lse = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True)
+    dout = torch.randn(out.shape, device="cuda").bfloat16()
+    dq, dk, dv, _ = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc)
+    assert all(torch.isfinite(t.float()).all() for t in (dq, dk, dv))
+    for b in (0, 31, 63):
+        one = {n: (t[b:b + 1] if torch.is_tensor(t) and t.shape[0] == B else t) for n, t in inp.items()}
+        one["extr_q"], one["coord_q"] = one["extr_k"], one["coord_k"]
+        reps1 = _dev_reps(cfg, one)
+        q1, k1, v1 = (x[b:b + 1] for x in (q, k, v))
+        o1, l1 = ops.gta_attention_fwd(q1, k1, v1, reps1, cfg.f_dims, trans_coeff=tc, return_lse=True)
+        g1 = ops.gta_attention_bwd(dout[b:b + 1], q1, k1, v1, o1, l1, reps1, cfg.f_dims, trans_coeff=tc, flags=_lib.GTA_FLAG_SINGLE_LAUNCH)
+        assert torch.equal(o1, out[b:b + 1])
+        assert torch.equal(g1[1], dk[b:b + 1]) and torch.equal(g1[2], dv[b:b + 1]), b
+        err = float((g1[0].float() - dq[b:b + 1].float()).abs().max())
+        assert err <= 2 ** -7 * float(dq[b:b + 1].float().abs().max()), (b, err)        # one bf16 ulp of the largest entry
+    del q, k, v, out, lse, dout, dq, dk, dv
+    cfg = GtaConfig(**MSN_SO3, n_q_views=2, n_k_views=2)
+    inp = make_inputs(cfg, 1, 4096, 4096, cross=False, seed=72, dtype=torch.bfloat16)
+    reps = _dev_reps(cfg, inp)
+    q, k, v = (inp[n].cuda() for n in "qkv")
+    out, lse = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, return_lse=True)
+    dout = torch.randn(out.shape, device="cuda").bfloat16()
+    fused = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc)
+    pair = ops.gta_attention_bwd(dout, q, k, v, out, lse, reps, cfg.f_dims, trans_coeff=tc, flags=_lib.GTA_FLAG_BWD_SPLIT)
+    for name, a, b_ in zip(("dq", "dk", "dv"), fused[:3], pair[:3]):
+        scale_ = float(b_.float().abs().max())
+        err = float((a.float() - b_.float()).abs().max())
+        print(f"L=8192 {name}: fused vs pair max-abs {err:.3e} (scale {scale_:.3e})")
+        assert err <= 1e-2 * scale_ + 1e-4, (name, err, scale_)
+    assert abs(float(fused[3]) - float(pair[3])) <= 1e-2 * max(1.0, abs(float(pair[3])))
+
+
 def test_host_pipeline_matches_device_call():
     """gta_b200.host.HostStagedAttention (pinned host buffers, batch chunks over three streams) is bit-identical to the
     device-resident call on the same inputs, for self- and cross-attention."""
