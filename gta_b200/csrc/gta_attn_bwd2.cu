@@ -10,8 +10,9 @@
 //     dV' += P^T dO'_i    (A = P^T as bf16 in tensor memory, B = dO'_i read MN-major)
 //     dK' += dS^T Q'_i    (A = dS^T from shared memory, K-major, 128-byte swizzle)
 //     dQ'_i(partial) = dS K'_j   (A = the SAME shared-memory tile read MN-major, B = K'_j read MN-major)
-//   The dQ' partial is drained from tensor memory by a reducer warpgroup into a shared-memory tile and added to an fp32
-//   accumulation buffer in global memory by ONE bulk reduction (cp.reduce.async.bulk ... add.f32, performed in L2); the
+//   The dQ' partial is drained from tensor memory by a reducer warpgroup, in two halves through one half-size shared-memory
+//   tile, and added to an fp32 accumulation buffer in global memory by bulk reductions (cp.reduce.async.bulk ... add.f32,
+//   performed in L2); the
 //   buffer's tile layout [D/4][128 rows][4 floats] is chosen so that both the staging writes and the finishing kernel's
 //   reads are conflict-free / coalesced.  bwd_dq_finish_kernel then applies rho_q^{-1} (and the query-side trans_coeff
 //   term) and writes dq.
@@ -20,7 +21,8 @@
 // dQ' shares its columns with dP^T: dP^T(i) is dead once dS(i) is computed, and dP^T(i+1) is issued when the reducer has
 // drained dQ'(i) — which happens while dV'(i) executes.  Issue order: S^T(i+1) as soon as S^T(i) is in registers; then, when P^T / dS^T
 // of pair i are ready, dQ'(i), dV'(i), dP^T(i+1), dK'(i).
-// Shared memory (D = 96): K', V' 48 KB | Q', dO' x 2 stages 96 KB | dS^T 32 KB | dQ' staging 48 KB | statistics 2 KB.
+// Shared memory (D = 96, 226 KB): K', V' 48 KB | Q' ring of 3 72 KB | dO' ring of 2 48 KB | dQ' staging 24 KB | dS^T 32 KB |
+// per-column statistics 2 KB.  The shared-memory pipe is the busiest unit of the kernel.
 //
 // 512 threads: warps 0-7 compute (setmaxnreg 184), warps 8-11 reducer (88), warp 12 UMMA issuer, warp 13 bulk-copy
 // producer, warps 14-15 only complete the warpgroup (56).
