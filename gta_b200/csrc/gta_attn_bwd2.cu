@@ -30,6 +30,13 @@
 
 namespace gta {
 
+// Share of the exponentials evaluated with poly_exp2x2 instead of MUFU.EX2: groups of 4 columns with (u4 % DEN) < NUM.
+#ifndef GTA_BWD2_POLY_NUM
+#define GTA_BWD2_POLY_NUM 0
+#endif
+#ifndef GTA_BWD2_POLY_DEN
+#define GTA_BWD2_POLY_DEN 4
+#endif
 constexpr int kFThreads = 512;
 constexpr uint32_t kFTmemS = 0, kFTmemDP = 128, kFTmemDV = 256, kFTmemDK = 352, kFTmemP = 448;
 constexpr uint32_t kSmemOptinMax = 232448u;   // 227 KB
@@ -194,10 +201,18 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const BwdA
 #endif
                 const uint64_t x01 = ffma2(pack_f32x2(__uint_as_float(sr[4 * u4]), __uint_as_float(sr[4 * u4 + 1])), cs2, l4.x);
                 const uint64_t x23 = ffma2(pack_f32x2(__uint_as_float(sr[4 * u4 + 2]), __uint_as_float(sr[4 * u4 + 3])), cs2, l4.y);
-                float x0, x1, x2, x3;
-                unpack_f32x2(x01, x0, x1);
-                unpack_f32x2(x23, x2, x3);
-                const float p0 = fast_exp2(x0), p1 = fast_exp2(x1), p2 = fast_exp2(x2), p3 = fast_exp2(x3);
+                float p0, p1, p2, p3;
+                if ((u4 % GTA_BWD2_POLY_DEN) < GTA_BWD2_POLY_NUM) {
+                    // a share of the exponentials on the FMA pipe (degree-3 polynomial, 7.5e-5 relative): the two compute warps of
+                    // a scheduler need 1024 clk of MUFU per pair otherwise
+                    poly_exp2x2(x01, p0, p1);
+                    poly_exp2x2(x23, p2, p3);
+                } else {
+                    float x0, x1, x2, x3;
+                    unpack_f32x2(x01, x0, x1);
+                    unpack_f32x2(x23, x2, x3);
+                    p0 = fast_exp2(x0); p1 = fast_exp2(x1); p2 = fast_exp2(x2); p3 = fast_exp2(x3);
+                }
                 sr[4 * u4] = __float_as_uint(p0); sr[4 * u4 + 1] = __float_as_uint(p1);
                 sr[4 * u4 + 2] = __float_as_uint(p2); sr[4 * u4 + 3] = __float_as_uint(p3);
                 pk[2 * u4] = pack_bf16x2(p0, p1); pk[2 * u4 + 1] = pack_bf16x2(p2, p3);
