@@ -177,7 +177,11 @@ def gta_attention_bwd(dout: torch.Tensor, q: torch.Tensor, k: torch.Tensor, v: t
                       debug_clocks: Optional[torch.Tensor] = None, flags: int = 0, euclid: bool = False):
     """Backward of gta_attention_fwd.  `out` is the forward result ([B,H,Tq,D] view of a [B,Tq,H,D] buffer), `lse` its
     log-sum-exp, `dout` the gradient w.r.t. `out` (any layout).  Returns (dq, dk, dv, dtrans_coeff) with dq/dk/dv shaped
-    like q/k/v (views of contiguous [B,T,H,D] buffers) and dtrans_coeff a [1] fp32 tensor (None without an se3 block)."""
+    like q/k/v (views of contiguous [B,T,H,D] buffers) and dtrans_coeff a [1] fp32 tensor (None without an se3 block).
+    Head dims <= 96 run ONE fused kernel (dK, dV, bulk-reduced dQ partial sums) + a dq finishing kernel; `flags`:
+    GTA_FLAG_BWD_SPLIT keeps the dK/dV + dQ kernel pair, GTA_FLAG_SINGLE_LAUNCH forces the fused kernel for calls of less than
+    one wave of key tiles, GTA_FLAG_RUNTIME_LAYOUT its run-time-layout epilogue.  `euclid` / a t2 block / unaligned blocks: the
+    element-wise rep passes around the same kernels (generic path)."""
     B, H, Tq, D = q.shape
     Tk = k.shape[2]
     dev = q.device
