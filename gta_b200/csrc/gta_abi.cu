@@ -64,7 +64,8 @@ using namespace gta;
 extern "C" {
 
 const char* gta_last_error(void) { return g_err; }
-int gta_abi_version(void) { return 4; }
+// 5: gta_attn_bwd_workspace_bytes_p, backward of the generic-path layouts, fused backward kernel (larger backward workspace)
+int gta_abi_version(void) { return 5; }
 
 size_t gta_attn_fwd_workspace_bytes(int B, int H, int Tk, int D) {
     if (B <= 0 || H <= 0 || Tk <= 0 || D <= 0) return 0;

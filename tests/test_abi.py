@@ -23,11 +23,24 @@ def test_header_and_binding_agree():
     assert sorted(_lib.SYMBOLS) == decl
 
 
+def test_flag_constants_match_header():
+    """The GTA_FLAG_* / GTA_ERR_* / GTA_DTYPE_* values of the ctypes binding are the header's."""
+    txt = open(os.path.join(ROOT, "include", "gta_b200.h")).read()
+    defs = dict(re.findall(r"#define\s+(GTA_(?:FLAG|ERR|DTYPE)_[A-Z0-9_]+)\s+\(?(-?\d+)\)?", txt))
+    assert "GTA_FLAG_BWD_SPLIT" in defs and "GTA_FLAG_SINGLE_LAUNCH" in defs
+    for name, val in defs.items():
+        if hasattr(_lib, name):
+            assert getattr(_lib, name) == int(val), name
+    for name in dir(_lib):
+        if name.startswith("GTA_FLAG_"):
+            assert name in defs, name
+
+
 def test_library_exports_every_declared_symbol():
     l = _lib.lib()
     for name in _declared_symbols():
         assert hasattr(l, name), name
-    assert l.gta_abi_version() == 4
+    assert l.gta_abi_version() == 5
 
 
 def test_struct_layout_matches_header_order():
