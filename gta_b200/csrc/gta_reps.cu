@@ -82,10 +82,9 @@ __device__ void wigner_d12(const double* R, float* d1, float* d2) {
 }
 
 // One thread per view.  side 0: query views (se3 = E), side 1: key views (se3 = inv(E)).
-__global__ void build_view_reps_kernel(const float* __restrict__ extr_q, const float* __restrict__ extr_k, int nq,
-                                       int nk, int want_so3, float* __restrict__ se3_q, float* __restrict__ se3_k,
-                                       float* __restrict__ so3_q, float* __restrict__ so3_k) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void build_view_reps(int i, const float* __restrict__ extr_q, const float* __restrict__ extr_k, int nq,
+                                                int nk, int want_so3, float* __restrict__ se3_q, float* __restrict__ se3_k,
+                                                float* __restrict__ so3_q, float* __restrict__ so3_k) {
     if (i >= nq + nk) return;
     const bool key = i >= nq;
     const int v = key ? i - nq : i;
@@ -105,10 +104,9 @@ __global__ void build_view_reps_kernel(const float* __restrict__ extr_q, const f
 
 // theta = fp32(max_freq * 2*pi) * fp32(coord * freq_j), freq_j = 2^(j+1)/2^n (gta.py:57-63); pair index
 // j*2 + axis (gta.py:68 + encoder.py:195).  One thread per (token, pair).
-__global__ void so2_table_kernel(const float* __restrict__ coord, int64_t ntok, int nfreqs, float wh, float ww,
-                                 int shared, float* __restrict__ cs /* [ntok, 2*nfreqs, 2] */,
-                                 float* __restrict__ mats /* [ntok, 2*nfreqs, 2, 2] or null */) {
-    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void so2_table(int64_t i, const float* __restrict__ coord, int64_t ntok, int nfreqs, float wh, float ww,
+                                          int shared, float* __restrict__ cs /* [ntok, 2*nfreqs, 2] */,
+                                          float* __restrict__ mats /* [ntok, 2*nfreqs, 2, 2] or null */) {
     const int C = 2 * nfreqs;
     if (i >= ntok * C) return;
     const int64_t t = i / C;
@@ -119,6 +117,33 @@ __global__ void so2_table_kernel(const float* __restrict__ coord, int64_t ntok, 
     sincosf(th, &s, &c);
     if (cs) { cs[i * 2] = c; cs[i * 2 + 1] = s; }
     if (mats) { mats[i * 4] = c; mats[i * 4 + 1] = -s; mats[i * 4 + 2] = s; mats[i * 4 + 3] = c; }
+}
+
+__global__ void so2_table_kernel(const float* __restrict__ coord, int64_t ntok, int nfreqs, float wh, float ww, int shared,
+                                 float* __restrict__ cs, float* __restrict__ mats) {
+    so2_table(static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x, coord, ntok, nfreqs, wh, ww, shared, cs, mats);
+}
+
+// pre_compute_reps in ONE launch: blocks [0, nb_view) build the per-view tables (one thread per view), the next nb_q blocks
+// the query-side SO(2) table, the rest the key-side one (three back-to-back launches of ~7-12 us each were 3.6 % of the
+// headline step; the parts are independent).
+struct BuildRepsArgs {
+    const float* extr_q; const float* extr_k; const float* coord_q; const float* coord_k;
+    int nq, nk, want_so3;
+    float* se3_q; float* se3_k; float* so3_q; float* so3_k; float* so2_q; float* so2_k;
+    int64_t ntok_q, ntok_k;
+    int nfreqs, shared;
+    float wh, ww;
+    unsigned nb_view, nb_q;
+};
+__global__ void __launch_bounds__(256) build_reps_kernel(const BuildRepsArgs a) {
+    if (blockIdx.x < a.nb_view) {
+        build_view_reps(blockIdx.x * 256 + threadIdx.x, a.extr_q, a.extr_k, a.nq, a.nk, a.want_so3, a.se3_q, a.se3_k, a.so3_q, a.so3_k);
+    } else if (blockIdx.x < a.nb_view + a.nb_q) {
+        so2_table(static_cast<int64_t>(blockIdx.x - a.nb_view) * 256 + threadIdx.x, a.coord_q, a.ntok_q, a.nfreqs, a.wh, a.ww, a.shared, a.so2_q, nullptr);
+    } else {
+        so2_table(static_cast<int64_t>(blockIdx.x - a.nb_view - a.nb_q) * 256 + threadIdx.x, a.coord_k, a.ntok_k, a.nfreqs, a.wh, a.ww, a.shared, a.so2_k, nullptr);
+    }
 }
 
 // torch.linalg.inv of a batch of 4x4 extrinsics (source/encoder.py:219).
@@ -151,25 +176,27 @@ int launch_build_reps(const float* extr_q, const float* extr_k, const float* coo
     if (B <= 0 || Nq <= 0 || Nk <= 0) return set_error(GTA_ERR_INVALID, "gta_build_reps: empty batch/views");
     if (so3_maxdeg != 0 && so3_maxdeg != 2)
         return set_error(GTA_ERR_UNSUPPORTED, "gta_build_reps: only so3 max degree 2 is implemented");
+    BuildRepsArgs a{};
     if (extr_q && extr_k && (se3_q || se3_k || so3_q || so3_k)) {
-        int n = B * (Nq + Nk);
-        build_view_reps_kernel<<<(n + 63) / 64, 64, 0, st>>>(extr_q, extr_k, B * Nq, B * Nk, so3_maxdeg == 2, se3_q,
-                                                             se3_k, so3_q, so3_k);
+        a.extr_q = extr_q; a.extr_k = extr_k; a.nq = B * Nq; a.nk = B * Nk; a.want_so3 = so3_maxdeg == 2;
+        a.se3_q = se3_q; a.se3_k = se3_k; a.so3_q = so3_q; a.so3_k = so3_k;
+        a.nb_view = static_cast<unsigned>((a.nq + a.nk + 255) / 256);
     }
+    unsigned nb_k = 0;
     if (so2_nfreqs > 0) {
-        const float wh = two_pi_times(mfh), ww = two_pi_times(mfw);
+        a.wh = two_pi_times(mfh); a.ww = two_pi_times(mfw); a.nfreqs = so2_nfreqs; a.shared = shared;
         const int C = 2 * so2_nfreqs;
         if (so2_q && coord_q) {
-            int64_t n = static_cast<int64_t>(B) * Tq * C;
-            so2_table_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-                coord_q, static_cast<int64_t>(B) * Tq, so2_nfreqs, wh, ww, shared, so2_q, nullptr);
+            a.coord_q = coord_q; a.so2_q = so2_q; a.ntok_q = static_cast<int64_t>(B) * Tq;
+            a.nb_q = static_cast<unsigned>((a.ntok_q * C + 255) / 256);
         }
         if (so2_k && coord_k && so2_k != so2_q) {
-            int64_t n = static_cast<int64_t>(B) * Tk * C;
-            so2_table_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-                coord_k, static_cast<int64_t>(B) * Tk, so2_nfreqs, wh, ww, shared, so2_k, nullptr);
+            a.coord_k = coord_k; a.so2_k = so2_k; a.ntok_k = static_cast<int64_t>(B) * Tk;
+            nb_k = static_cast<unsigned>((a.ntok_k * C + 255) / 256);
         }
     }
+    const unsigned nb = a.nb_view + a.nb_q + nb_k;
+    if (nb) build_reps_kernel<<<nb, 256, 0, st>>>(a);
     return check_launch("gta_build_reps");
 }
 
