@@ -67,6 +67,68 @@ struct AttnArgs {
 };
 
 
+// "Optimistic" softmax of one 128-column score tile: the exponentials are taken against the row's CURRENT reference maximum
+// m_used (lazy rescaling lets a tile exceed it by up to 2^threshold), so they can start as soon as the first 32 score columns
+// are in registers -- the tcgen05.ld of the next quarter is in flight while a quarter is exponentiated, and the tile maximum
+// is computed alongside on the ALU pipe instead of in front of the first MUFU op.  Only after the last quarter is the maximum
+// checked: if no row of the warp needs its reference advanced, P (bf16, packed in place over the registers the scores came in)
+// is stored over S and the row sum is added to l_run -- bit-identical to the load-all / max / exp sequence of the caller.
+// Otherwise nothing has been written (S is intact in tensor memory, sreg is clobbered, l_run untouched) and the caller runs
+// that sequence for the tile.  Requires a finite m_used (not the first tile of an item) and a full tile (no masked columns).
+// MEASURED SLOWER and therefore compiled out by default (GTA_OPTIMISTIC=1 enables it; profiles/r02_optimistic_softmax_ab.txt):
+// attention kernel 0.430 vs 0.402 ms at MSN B=64, parity green.  ptxas already streams the four tcgen05.ld of the plain
+// sequence through the scoreboard (tcgen05.wait::ld emits no instruction), and starting the exponentials earlier only makes
+// the two warpgroups overlap their MUFU phases more: the loop is bound by the 16 MUFU lanes, not by what precedes them.
+template <int kPolyNum, int kPolyDen>
+__device__ __forceinline__ bool softmax_tile_optimistic(const uint32_t s_addr, uint32_t* sreg, const float m_used,
+                                                        const float cs, const uint64_t cs2, const float threshold,
+                                                        float& l_run) {
+    float* s = reinterpret_cast<float*>(sreg);
+    const float neg = -m_used * cs;
+    const uint64_t neg2 = pack_f32x2(neg, neg);
+    uint64_t lsum2 = pack_f32x2(0.f, 0.f);
+    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;     // maxima of x = (s - m_used) * cs
+    tmem_ld32(s_addr, sreg);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        tmem_ld_wait32(sreg + q * 32);
+        if (q < 3) tmem_ld32(s_addr + (q + 1) * 32, sreg + (q + 1) * 32);
+        // same in-place packing as the caller's sequence: pair il of half h reads s[h*64 + 2il], s[h*64 + 2il + 1] and
+        // lands in sreg[h*64 + il] (a register of this or the previous quarter, never one a load in flight is writing).
+        // The maximum is taken over the scaled differences x (a score register dies with its FFMA2, as in the caller's
+        // sequence: taking it over s kept both alive and spilled inside the loop at 184 registers).
+        const int h = q >> 1;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int il = (q & 1) * 16 + k;
+            const uint64_t x2 = ffma2(pack_f32x2(s[h * 64 + 2 * il], s[h * 64 + 2 * il + 1]), cs2, neg2);
+            float x0, x1;
+            unpack_f32x2(x2, x0, x1);
+            if ((k & 3) == 0) mx0 = fmax3(mx0, x0, x1);
+            else if ((k & 3) == 1) mx1 = fmax3(mx1, x0, x1);
+            else if ((k & 3) == 2) mx2 = fmax3(mx2, x0, x1);
+            else mx3 = fmax3(mx3, x0, x1);
+            float p0, p1;
+            if ((il % kPolyDen) < kPolyNum) {
+                poly_exp2x2(x2, p0, p1);
+            } else {
+                p0 = fast_exp2(x0); p1 = fast_exp2(x1);
+            }
+            lsum2 = fadd2(lsum2, pack_f32x2(p0, p1));
+            sreg[h * 64 + il] = pack_bf16x2(p0, p1);
+        }
+    }
+    // (s - m_used) * cs > threshold for some column <=> the caller's test on the tile maximum (up to the rounding of the FMA)
+    const bool grow = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) > threshold;
+    if (__any_sync(0xffffffffu, grow)) return false;
+    tmem_st32(s_addr, sreg);
+    tmem_st32(s_addr + 32, sreg + 64);
+    float ls0, ls1;
+    unpack_f32x2(lsum2, ls0, ls1);
+    l_run += ls0 + ls1;
+    return true;
+}
+
 inline AttnArgs make_attn_args(const GtaAttnParams& p) {
     AttnArgs a;
     a.q = p.q; a.q_sb = p.q_stride_b; a.q_sh = p.q_stride_h; a.q_st = p.q_stride_t;

@@ -34,6 +34,9 @@ constexpr float k3RescaleThreshold = 8.0f;   // log2 units
 #ifndef GTA_POLY_DEN
 #define GTA_POLY_DEN 4
 #endif
+#ifndef GTA_OPTIMISTIC
+#define GTA_OPTIMISTIC 0
+#endif
 
 template <int D>
 struct Attn3Cfg {
@@ -160,6 +163,17 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                 if (dbg) d_wait_s += clock64() - d_w0;
                 tc_fence_after();
                 uint32_t sreg[128];
+#if GTA_OPTIMISTIC
+                // measured variant, off by default (softmax_tile_optimistic, attn_common.cuh): every full tile after the
+                // item's first takes its exponentials against the current reference while the scores still stream in
+                if (j > 0 && (j < n - 1 || a.Tk - j * 128 == 128) &&
+                    softmax_tile_optimistic<GTA_POLY_NUM, GTA_POLY_DEN>(s_addr, sreg, m_used, cs, cs2, k3RescaleThreshold, l_run)) {
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&bars[L::bPFull + X]);
+                    continue;
+                }
+#endif
                 tmem_ld32(s_addr, sreg);
                 tmem_ld32(s_addr + 32, sreg + 32);
                 tmem_ld32(s_addr + 64, sreg + 64);
