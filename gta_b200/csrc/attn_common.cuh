@@ -64,6 +64,7 @@ struct AttnArgs {
     float scale, scale_log2;
     int v_transform;
     long long* dbg;
+    int so2_stage;      // attn_fwd3_kernel: row stride (floats) of the per-warp SO(2) staging rows in shared memory, 0 = off
 };
 
 
@@ -145,6 +146,7 @@ inline AttnArgs make_attn_args(const GtaAttnParams& p) {
     a.scale_log2 = p.scale * 1.4426950408889634f;
     a.v_transform = p.v_transform;
     a.dbg = p.debug_clocks;
+    a.so2_stage = 0;
     return a;
 }
 

@@ -37,6 +37,16 @@ constexpr float k3RescaleThreshold = 8.0f;   // log2 units
 #ifndef GTA_OPTIMISTIC
 #define GTA_OPTIMISTIC 0
 #endif
+// Q stager: L1 prefetch of the next row (head dims <= 64), see the stager loop.
+#ifndef GTA_Q_ROW_PREFETCH
+#define GTA_Q_ROW_PREFETCH 1
+#endif
+constexpr bool kQRowPrefetch = GTA_Q_ROW_PREFETCH != 0;
+// Epilogue: SO(2) table rows staged in shared memory by coalesced asynchronous copies (see the softmax loop's last key tile).
+#ifndef GTA_SO2_STAGE
+#define GTA_SO2_STAGE 1
+#endif
+constexpr bool kSo2Stage = GTA_SO2_STAGE != 0;
 
 template <int D>
 struct Attn3Cfg {
@@ -62,6 +72,10 @@ struct Attn3Cfg {
     static constexpr uint32_t kTmemSlot = kBars + bCount * 8;
     static constexpr uint32_t kUsed = kTmemSlot + 16;
     static constexpr uint32_t kBytes = (kUsed + 1024 > 120u * 1024u) ? kUsed + 1024 : 120u * 1024u;
+    // Optional tail (launch3_one adds it to the dynamic size when it fits): per softmax warp 32 rows of the tokens' SO(2)
+    // (cos, sin) table, row stride so2 + 4 floats (conflict-free 16-byte reads of a thread's own row).
+    static constexpr uint32_t kSo2 = (kUsed + 15u) & ~15u;
+    static constexpr uint32_t so2_stage_bytes(int so2_dims) { return 8u * 32u * static_cast<uint32_t>(so2_dims + 4) * 4u; }
 };
 
 struct ItemCoord {
@@ -129,6 +143,9 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
         const uint32_t o_addr = lane_base + (X ? k3TmemOB : k3TmemOA);
         const float cs = a.scale_log2;
         const uint64_t cs2 = pack_f32x2(cs, cs);
+        // SO(2) staging rows of this warp / of this thread's query row (null: the epilogue reads the table from global memory)
+        float* so2_sm_warp = reinterpret_cast<float*>(smem + L::kSo2) + warp * 32 * a.so2_stage;
+        const float* so2_sm = a.so2_stage ? so2_sm_warp + lane * a.so2_stage : nullptr;
         uint32_t gt = 0;      // tiles processed by this warpgroup (s_full / p_full phase)
         uint32_t cnt = 0;     // items processed by this warpgroup (o_final phase)
         // optional phase clocks (GtaAttnParams.debug_clocks): [cta][16] accumulated over the CTA's items
@@ -153,7 +170,24 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                     const size_t view_ = static_cast<size_t>(ic.b) * a.Nq + tt_ / a.tpvq;
                     if (a.hd.se3) prefetch_l1(a.se3_q + view_ * 16);
                     if (a.hd.so3) { prefetch_l1(a.so3_q + view_ * 34); prefetch_l1(a.so3_q + view_ * 34 + 32); }
-                    if (a.hd.so2) {
+                    if (a.hd.so2 && so2_sm) {
+                        // the warp's 32 token rows of the SO(2) table are one contiguous block: copy it with coalesced 16-byte
+                        // asynchronous copies (lane = consecutive float4) instead of letting every thread fetch its own row in
+                        // the epilogue (a warp-wide LDG.128 of 32 different lines costs 32 L1 wavefronts: the so2 chunks took
+                        // 830 clk each against 270 for the SE(3) chunks)
+                        __syncwarp();                            // every lane is done with the previous item's rows
+                        const int q4 = a.hd.so2 >> 2;            // float4 per token
+                        const int tb = ic.p * 256 + X * 128 + (warp & 3) * 32;
+                        const int dq = 32 / q4, dm = 32 - dq * q4;
+                        int row = lane / q4, col = lane - row * q4;
+                        for (int i = 0; i < q4; ++i) {
+                            const int tk_ = tb + row < a.Tq ? tb + row : a.Tq - 1;
+                            cp_async16(so2_sm_warp + row * a.so2_stage + col * 4,
+                                       a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tk_) * a.hd.so2 + col * 4);
+                            col += dm; row += dq;
+                            if (col >= q4) { col -= q4; ++row; }
+                        }
+                    } else if (a.hd.so2) {
                         const float* so2_ = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt_) * a.C * 2;
                         for (int off = 0; off < a.C * 2; off += 32) prefetch_l1(so2_ + off);
                     }
@@ -336,11 +370,24 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                     }
                 }
                 if (dbg) e2 = clock64();
-                So2Chunk sc_cur = load_so2_chunk(so2, c_so2, a.hd);
+                auto get_so2 = [&](int c) {
+                    if (so2_sm) {
+                        So2Chunk r_;
+                        const float4* p_ = reinterpret_cast<const float4*>(so2_sm + (c - c_so2) * 8);
+                        r_.a = p_[0]; r_.b = p_[1];
+                        return r_;
+                    }
+                    return load_so2_chunk(so2, c, a.hd);
+                };
+                if (so2_sm && c_so2 < D / 8) {
+                    cp_async_wait_all();
+                    __syncwarp();
+                }
+                So2Chunk sc_cur = get_so2(c_so2);
 #pragma unroll 1
                 for (int c = c_so2; c < D / 8; ++c) {
                     So2Chunk sc_nxt = sc_cur;
-                    if (c + 1 < D / 8) sc_nxt = load_so2_chunk(so2, c + 1, a.hd);
+                    if (c + 1 < D / 8) sc_nxt = get_so2(c + 1);
                     float x[8];
                     next_o(c, x);
                     const float cs8[8] = {sc_cur.a.x, sc_cur.a.y, sc_cur.a.z, sc_cur.a.w, sc_cur.b.x, sc_cur.b.y, sc_cur.b.z, sc_cur.b.w};
@@ -385,6 +432,24 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                     const int t = ic.p * 256 + X * 128 + r;
                     const bool valid = t < a.Tq;
                     const int tt = valid ? t : a.Tq - 1;
+                    if constexpr (kQRowPrefetch && D <= 64) {
+                        // Short key loops (CLEVR: 5 key tiles per item) leave the two stager warps less time per item than
+                        // their four dependent load round trips take (q_full was 31 % of the issuer's time at the CLEVR decoder
+                        // shape): pull the NEXT row this thread will stage -- its raw q line and its SO(2) table line -- into L1
+                        // now.  Only where shared memory leaves L1 room (D <= 64).
+                        int nb_ = ic.b, nh_ = ic.h, nt_ = -1;
+                        if (rr == 0) nt_ = t + 64;
+                        else if (X == 0 && ic.has_b) nt_ = ic.p * 256 + 128 + r0;
+                        else if (item + static_cast<int>(gridDim.x) < nitems) {
+                            const ItemCoord nx_ = decode_item(item + gridDim.x, npairs, a.H, a.Tq);
+                            nb_ = nx_.b; nh_ = nx_.h; nt_ = nx_.p * 256 + r0;
+                        }
+                        if (nt_ >= 0 && nt_ < a.Tq) {
+                            prefetch_l1(reinterpret_cast<const TIn*>(a.q) + static_cast<int64_t>(nb_) * a.q_sb +
+                                        static_cast<int64_t>(nh_) * a.q_sh + static_cast<int64_t>(nt_) * a.q_st);
+                            if (a.hd.so2) prefetch_l1(a.so2_q + (static_cast<size_t>(nb_) * a.Tq + nt_) * a.C * 2);
+                        }
+                    }
                     const size_t view = static_cast<size_t>(ic.b) * a.Nq + tt / a.tpvq;
                     const float* so2 = a.so2_q + (static_cast<size_t>(ic.b) * a.Tq + tt) * a.C * 2;
                     const TIn* qrow = reinterpret_cast<const TIn*>(a.q) + static_cast<int64_t>(ic.b) * a.q_sb +
@@ -534,10 +599,18 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
 }
 
 template <typename TIn, typename TOut, int D>
-static int launch3_one(const AttnArgs& a, const GtaAttnParams& p, cudaStream_t st) {
+static int launch3_one(const AttnArgs& a_in, const GtaAttnParams& p, cudaStream_t st) {
     using L = Attn3Cfg<D>;
     auto kern = attn_fwd3_kernel<TIn, TOut, D>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(L::kBytes));
+    // SO(2) staging rows behind the fixed layout when they fit the 227 KB of a CTA (MSN: 24 so2 dims -> 28 KB, CLEVR: 32 -> 36 KB)
+    AttnArgs a = a_in;
+    uint32_t smem_bytes = L::kBytes;
+    if (kSo2Stage && p.so2 > 0 && p.v_transform && L::kSo2 + L::so2_stage_bytes(p.so2) + 1024u <= 227u * 1024u) {
+        a.so2_stage = p.so2 + 4;
+        const uint32_t need = L::kSo2 + L::so2_stage_bytes(p.so2) + 1024u;
+        if (need > smem_bytes) smem_bytes = need;
+    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(227u * 1024u));
     if (e != cudaSuccess) return set_error(GTA_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     static int num_sms = 0;
     if (num_sms == 0) {
@@ -550,7 +623,7 @@ static int launch3_one(const AttnArgs& a, const GtaAttnParams& p, cudaStream_t s
     const long long nitems = static_cast<long long>(p.B) * p.H * npairs;
     if (nitems > 0x7fffffffLL) return set_error(GTA_ERR_UNSUPPORTED, "too many work items");
     const int grid = static_cast<int>(nitems < num_sms ? nitems : num_sms);
-    kern<<<grid, kThreads3, L::kBytes, st>>>(a, npairs, static_cast<int>(nitems));
+    kern<<<grid, kThreads3, smem_bytes, st>>>(a, npairs, static_cast<int>(nitems));
     return check_launch("gta_attn_fwd");
 }
 
