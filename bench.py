@@ -502,8 +502,8 @@ def main():
     _q, _k, _v = views(dev_bufs)
     pipeline = ops.pipeline_of(_q, _k, _v, ops.PackedReps(n_q_views=nq, n_k_views=nk), cfg.f_dims, flags=args.flags)
     two_launch = pipeline != "single launch"
-    # kernels per step: build_view_reps (1) + so2 tables (1 self / 2 cross) + [staging (1)] + attention (1)
-    launches_per_step = 1 + (2 if cross else 1) + (2 if two_launch else 1)
+    # kernels per step: build_reps_kernel (1: view tables + both SO(2) tables) + [staging (1)] + attention (1)
+    launches_per_step = 1 + (2 if two_launch else 1)
 
     def barrier():
         if dist is not None:

@@ -43,8 +43,12 @@ constexpr float k3RescaleThreshold = 8.0f;   // log2 units
 #endif
 constexpr bool kQRowPrefetch = GTA_Q_ROW_PREFETCH != 0;
 // Epilogue: SO(2) table rows staged in shared memory by coalesced asynchronous copies (see the softmax loop's last key tile).
+// MEASURED, OFF BY DEFAULT (-DGTA_SO2_STAGE=1 compiles it in): the so2 section of the epilogue drops from 2.97 k to 1.82 k clk per
+// item at MSN, but the 28 KB of rows take the CTA from 198 to 226 KB of shared memory, i.e. they halve what is left of the
+// 256 KB array as L1 for the stager's and the epilogue's global loads: the whole step is 3.5 % SLOWER at the MSN encoder
+// shape (0.534 vs 0.516 ms, same box, profiles/r02_so2_stage_ab2.txt); neutral at D = 64 where shared memory is plentiful.
 #ifndef GTA_SO2_STAGE
-#define GTA_SO2_STAGE 1
+#define GTA_SO2_STAGE 0
 #endif
 constexpr bool kSo2Stage = GTA_SO2_STAGE != 0;
 
@@ -143,9 +147,6 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
         const uint32_t o_addr = lane_base + (X ? k3TmemOB : k3TmemOA);
         const float cs = a.scale_log2;
         const uint64_t cs2 = pack_f32x2(cs, cs);
-        // SO(2) staging rows of this warp / of this thread's query row (null: the epilogue reads the table from global memory)
-        float* so2_sm_warp = reinterpret_cast<float*>(smem + L::kSo2) + warp * 32 * a.so2_stage;
-        const float* so2_sm = a.so2_stage ? so2_sm_warp + lane * a.so2_stage : nullptr;
         uint32_t gt = 0;      // tiles processed by this warpgroup (s_full / p_full phase)
         uint32_t cnt = 0;     // items processed by this warpgroup (o_final phase)
         // optional phase clocks (GtaAttnParams.debug_clocks): [cta][16] accumulated over the CTA's items
@@ -170,7 +171,8 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                     const size_t view_ = static_cast<size_t>(ic.b) * a.Nq + tt_ / a.tpvq;
                     if (a.hd.se3) prefetch_l1(a.se3_q + view_ * 16);
                     if (a.hd.so3) { prefetch_l1(a.so3_q + view_ * 34); prefetch_l1(a.so3_q + view_ * 34 + 32); }
-                    if (a.hd.so2 && so2_sm) {
+                    if (kSo2Stage && a.hd.so2 && a.so2_stage) {
+                        float* so2_sm_warp = reinterpret_cast<float*>(smem + L::kSo2) + warp * 32 * a.so2_stage;
                         // the warp's 32 token rows of the SO(2) table are one contiguous block: copy it with coalesced 16-byte
                         // asynchronous copies (lane = consecutive float4) instead of letting every thread fetch its own row in
                         // the epilogue (a warp-wide LDG.128 of 32 different lines costs 32 L1 wavefronts: the so2 chunks took
@@ -370,6 +372,10 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
                     }
                 }
                 if (dbg) e2 = clock64();
+                // this thread's row of the SO(2) staging rows (null: the table is read from global memory)
+                const float* so2_sm = nullptr;
+                if (kSo2Stage && a.so2_stage)
+                    so2_sm = reinterpret_cast<const float*>(smem + L::kSo2) + (warp * 32 + lane) * a.so2_stage;
                 auto get_so2 = [&](int c) {
                     if (so2_sm) {
                         So2Chunk r_;

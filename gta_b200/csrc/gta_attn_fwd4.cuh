@@ -84,7 +84,7 @@ constexpr float k4RescaleThreshold = 8.0f;   // log2 units
 #endif
 // Epilogue: SO(2) table rows staged in shared memory by coalesced asynchronous copies (as in attn_fwd3_kernel).
 #ifndef GTA_SO2_STAGE
-#define GTA_SO2_STAGE 1
+#define GTA_SO2_STAGE 0
 #endif
 constexpr bool kSo2Stage4 = GTA_SO2_STAGE != 0;
 
@@ -324,9 +324,6 @@ __global__ void __launch_bounds__(kThreads4, 1) attn_fwd4_kernel(const AttnArgs 
         const uint32_t o_addr = lane_base + (X ? k4TmemOB : k4TmemOA);
         const float cs = a.scale_log2;
         const uint64_t cs2 = pack_f32x2(cs, cs);
-        // SO(2) staging rows of this warp / of this thread's query row (null: the epilogue reads the table from global memory)
-        float* so2_sm_warp = reinterpret_cast<float*>(smem + L::kSo2) + warp * 32 * a.so2_stage;
-        const float* so2_sm = a.so2_stage ? so2_sm_warp + lane * a.so2_stage : nullptr;
         uint32_t gt = 0;      // tiles processed by this warpgroup (s_full / p_full phase)
         uint32_t cnt = 0;     // items processed by this warpgroup (o_final phase)
         // optional phase clocks (GtaAttnParams.debug_clocks): [cta][16] accumulated over the CTA's items
@@ -351,7 +348,8 @@ __global__ void __launch_bounds__(kThreads4, 1) attn_fwd4_kernel(const AttnArgs 
                     const size_t view_ = static_cast<size_t>(ic.b) * a.Nq + tt_ / a.tpvq;
                     if (a.hd.se3) prefetch_l1(a.se3_q + view_ * 16);
                     if (a.hd.so3) { prefetch_l1(a.so3_q + view_ * 34); prefetch_l1(a.so3_q + view_ * 34 + 32); }
-                    if (a.hd.so2 && so2_sm) {
+                    if (kSo2Stage4 && D <= 64 && a.hd.so2 && a.so2_stage) {
+                        float* so2_sm_warp = reinterpret_cast<float*>(smem + L::kSo2) + warp * 32 * a.so2_stage;
                         // coalesced asynchronous copy of the warp's 32 SO(2) table rows into shared memory (attn_fwd3_kernel)
                         __syncwarp();
                         const int q4 = a.hd.so2 >> 2;
@@ -548,6 +546,10 @@ __global__ void __launch_bounds__(kThreads4, 1) attn_fwd4_kernel(const AttnArgs 
                     }
                 }
                 if (dbg) e2 = clock64();
+                // this thread's row of the SO(2) staging rows (null: the table is read from global memory)
+                const float* so2_sm = nullptr;
+                if (kSo2Stage4 && D <= 64 && a.so2_stage)
+                    so2_sm = reinterpret_cast<const float*>(smem + L::kSo2) + (warp * 32 + lane) * a.so2_stage;
                 auto get_so2 = [&](int c) {
                     if (so2_sm) {
                         So2Chunk r_;
@@ -833,9 +835,9 @@ static int launch4_one(const AttnArgs& a_in, const Fused4Args& f, const GtaAttnP
             kern = attn_fwd4_kernel<TIn, TOut, D, (D == 96 && sizeof(TIn) == 2 && sizeof(TOut) == 2 && std::is_void<LY>::value), LY>;
         else return set_error(GTA_ERR_UNSUPPORTED, "debug_clocks: bf16 in/out, head dim 96 only");
     }
-    // SO(2) staging rows behind the fixed layout -- head dims <= 64 only: at D = 96 the extra 28 KB leave the staging warps'
-    // global loads almost no L1 (measured on one box: MSN decoder 0.946 vs 0.892 ms, MSN encoder 0.598 vs 0.533 ms with the
-    // rows; CLEVR decoder 0.223 vs 0.227 ms), while attn_fwd3_kernel, whose K'/V' come from the staging kernel, gains 1-3 %
+    // SO(2) staging rows behind the fixed layout (-DGTA_SO2_STAGE=1, off by default: see gta_attn_fwd3.cu) -- head dims <= 64
+    // only: at D = 96 the extra 28 KB leave the staging warps' global loads almost no L1 (measured on one box: MSN decoder
+    // 0.946 vs 0.892 ms, MSN encoder 0.598 vs 0.533 ms with the rows); at D = 64 they are neutral (CLEVR decoder 0.214 ms either way)
     AttnArgs a = a_in;
     uint32_t smem_bytes = L::kBytes;
     if (kSo2Stage4 && D <= 64 && p.so2 > 0 && p.v_transform && L::kSo2 + L::so2_stage_bytes(p.so2) + 1024u <= 227u * 1024u) {

@@ -138,7 +138,11 @@ struct BuildRepsArgs {
 };
 __global__ void __launch_bounds__(256) build_reps_kernel(const BuildRepsArgs a) {
     if (blockIdx.x < a.nb_view) {
-        build_view_reps(blockIdx.x * 256 + threadIdx.x, a.extr_q, a.extr_k, a.nq, a.nk, a.want_so3, a.se3_q, a.se3_k, a.so3_q, a.so3_k);
+        // ONE warp of views per block (the other warps leave): the fp64 inverse / Euler / Wigner chain is bound by the SM's few
+        // fp64 lanes, so the views are spread over as many SMs as possible (with 256 views per block the merged launch was
+        // ~6 us slower than the three separate launches it replaced at the decoder shapes)
+        if (threadIdx.x < 32)
+            build_view_reps(blockIdx.x * 32 + threadIdx.x, a.extr_q, a.extr_k, a.nq, a.nk, a.want_so3, a.se3_q, a.se3_k, a.so3_q, a.so3_k);
     } else if (blockIdx.x < a.nb_view + a.nb_q) {
         so2_table(static_cast<int64_t>(blockIdx.x - a.nb_view) * 256 + threadIdx.x, a.coord_q, a.ntok_q, a.nfreqs, a.wh, a.ww, a.shared, a.so2_q, nullptr);
     } else {
@@ -180,7 +184,7 @@ int launch_build_reps(const float* extr_q, const float* extr_k, const float* coo
     if (extr_q && extr_k && (se3_q || se3_k || so3_q || so3_k)) {
         a.extr_q = extr_q; a.extr_k = extr_k; a.nq = B * Nq; a.nk = B * Nk; a.want_so3 = so3_maxdeg == 2;
         a.se3_q = se3_q; a.se3_k = se3_k; a.so3_q = so3_q; a.so3_k = so3_k;
-        a.nb_view = static_cast<unsigned>((a.nq + a.nk + 255) / 256);
+        a.nb_view = static_cast<unsigned>((a.nq + a.nk + 31) / 32);
     }
     unsigned nb_k = 0;
     if (so2_nfreqs > 0) {
