@@ -564,7 +564,7 @@ def main():
         h2d_bytes = in_bytes + sum(t.numel() * t.element_size() for t in dev_small.values())
         e2e = {"value": world * B * nq * tq / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": out_host.numel() * 2, "ms_per_step": ms_e2e, "steps": n_e2e,
-               "api": "gta_b200.host.HostStagedAttention.run: %d batch chunks, H2D / compute / D2H on three streams" % len(pipe.bounds)}
+               "api": "gta_b200.host.HostStagedAttention.run: %d batch chunks, H2D / compute / D2H on three streams, input copies of consecutive calls back to back" % len(pipe.bounds)}
 
     bwd = None
     if not args.no_backward:

@@ -5,6 +5,10 @@ or a data-loader-fed evaluation loop — the PCIe copies dominate (378 MB in, 12
 of GPU work), so this wrapper splits the batch into chunks and runs three streams: chunk c+1 is copied in while chunk c
 is computed and chunk c-1 is copied out (PCIe is full duplex).  Every (batch, head) is an independent attention problem
 and the reps depend only on the batch element, so chunking changes nothing numerically.
+
+Consecutive `run()` calls overlap as well: the host-to-device stream does not wait for the previous call to drain (its last
+chunk's compute and copy-out), only for the previous use of the device slot it overwrites, so the input copies — the
+bottleneck — run back to back across calls.
 """
 from __future__ import annotations
 
@@ -32,6 +36,11 @@ class HostStagedAttention:
         self.out_dev = torch.empty(out_host.shape, device=device, dtype=out_host.dtype)
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
         self.tc = torch.tensor([0.01], device=device)
+        # hazards across calls: slot c of dev_bufs is free once chunk c of the previous call was computed, slot c of out_dev
+        # once it was copied out, dev_small once the previous call's reps were built from it
+        self._ev_cmp = [None] * len(self.bounds)
+        self._ev_out = [None] * len(self.bounds)
+        self._ev_reps = None
 
     def _views(self, lo: int, hi: int):
         H, D = self.cfg.heads, self.cfg.head_dim
@@ -42,16 +51,21 @@ class HostStagedAttention:
         k, v = (hv(t) for t in self.dev_bufs["kv"][lo:hi].chunk(2, dim=-1))
         return q, k, v
 
-    def run(self, trans_coeff: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
-        """One forward over the whole host batch; returns `out_host` (valid after the current stream is synchronised)."""
+    def run(self, trans_coeff: Optional[torch.Tensor] = None, flags: int = 0, inputs_on_stream: bool = False) -> torch.Tensor:
+        """One forward over the whole host batch; returns `out_host` (valid after the current stream is synchronised).
+        The host buffers must hold their final contents when `run` is called (CPU-written, the normal case); pass
+        `inputs_on_stream=True` if they are being filled by work queued on the current stream, which then also orders the
+        input copies after it (and after the previous call)."""
         cfg = self.cfg
         cur = torch.cuda.current_stream(self.dev)
         start = torch.cuda.Event()
         start.record(cur)
-        for s in (self.s_in, self.s_cmp, self.s_out):
+        for s in (self.s_cmp, self.s_out) + ((self.s_in,) if inputs_on_stream else ()):
             s.wait_event(start)
         tc = self.tc if trans_coeff is None else trans_coeff
         with torch.cuda.stream(self.s_in):
+            if self._ev_reps is not None:
+                self.s_in.wait_event(self._ev_reps)
             for k_ in self.small_host:
                 self.dev_small[k_].copy_(self.small_host[k_], non_blocking=True)
             small_ready = torch.cuda.Event()
@@ -63,22 +77,32 @@ class HostStagedAttention:
             cq = self.dev_small.get("coord_q", ck)
             same = "extr_q" not in self.dev_small
             reps_all = ops.build_reps(ek if same else eq, ek, ck if same else cq, ck, so2_nfreqs=cfg.so2, so3_maxdeg=cfg.so3)
-        for lo, hi in self.bounds:
+            self._ev_reps = torch.cuda.Event()
+            self._ev_reps.record(self.s_cmp)
+        for ci, (lo, hi) in enumerate(self.bounds):
             with torch.cuda.stream(self.s_in):
+                if self._ev_cmp[ci] is not None:
+                    self.s_in.wait_event(self._ev_cmp[ci])
                 for k_ in self.bufs_host:
                     self.dev_bufs[k_][lo:hi].copy_(self.bufs_host[k_][lo:hi], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_in)
             with torch.cuda.stream(self.s_cmp):
                 self.s_cmp.wait_event(ev_in)
+                if self._ev_out[ci] is not None:
+                    self.s_cmp.wait_event(self._ev_out[ci])
                 q, k, v = self._views(lo, hi)
                 reps = reps_all.batch_slice(lo, hi)
                 o = ops.gta_attention_fwd(q, k, v, reps, cfg.f_dims, trans_coeff=tc, flags=flags, out=self.out_dev[lo:hi])
                 ev_cmp = torch.cuda.Event()
                 ev_cmp.record(self.s_cmp)
+                self._ev_cmp[ci] = ev_cmp
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_cmp)
                 self.out_host[lo:hi].copy_(self.out_dev[lo:hi], non_blocking=True)
+                ev_out = torch.cuda.Event()
+                ev_out.record(self.s_out)
+                self._ev_out[ci] = ev_out
         done = torch.cuda.Event()
         done.record(self.s_out)
         cur.wait_event(done)

@@ -718,6 +718,13 @@ def test_host_pipeline_matches_device_call():
         torch.cuda.synchronize()
         ref = _run(cfg, inp)                                  # [B,H,Tq,D]
         assert np.array_equal(out_host.permute(0, 2, 1, 3).float().numpy(), ref)
+        # back-to-back calls overlap (the input copies of a call do not wait for the previous call to drain): same result
+        out_host.zero_()
+        for _ in range(3):
+            pipe.run()
+        pipe.run(inputs_on_stream=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(out_host.permute(0, 2, 1, 3).float().numpy(), ref)
 
 
 @pytest.mark.parametrize("base", [MSN_SO3, CLEVR_T2], ids=["msn_so3", "clevr_t2"])
