@@ -37,6 +37,10 @@ constexpr float k3RescaleThreshold = 8.0f;   // log2 units
 #ifndef GTA_OPTIMISTIC
 #define GTA_OPTIMISTIC 0
 #endif
+// Q stager: raw q rows loaded with the L1 evict-first priority (measured variant, off by default).
+#ifndef GTA_Q_EVICT_FIRST
+#define GTA_Q_EVICT_FIRST 0
+#endif
 // Q stager: L1 prefetch of the next row (head dims <= 64), see the stager loop.
 #ifndef GTA_Q_ROW_PREFETCH
 #define GTA_Q_ROW_PREFETCH 1
@@ -470,7 +474,11 @@ __global__ void __launch_bounds__(kThreads3, 1) attn_fwd3_kernel(const AttnArgs 
 #pragma unroll
                         for (int i = 0; i < G; ++i) {
                             zero_raw(raw[i]);
+#if GTA_Q_EVICT_FIRST
+                            if (valid) load_raw_stream(qrow + (g * G + i) * 8, raw[i]);
+#else
                             if (valid) load_raw(qrow + (g * G + i) * 8, raw[i]);
+#endif
                         }
 #pragma unroll
                         for (int i = 0; i < G; ++i) {

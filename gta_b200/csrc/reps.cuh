@@ -265,6 +265,15 @@ __device__ __forceinline__ void load_raw(const float* __restrict__ p, RawChunk<f
     r.a = __ldg(reinterpret_cast<const float4*>(p));
     r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
 }
+// The same loads for rows that are read once (raw q rows of the Q stager): allocate in L1 for the thread's own neighbouring
+// chunks of the line, but as the first candidates for eviction, so that they do not push out the rep tables other warps reuse.
+__device__ __forceinline__ void load_raw_stream(const __nv_bfloat16* __restrict__ p, RawChunk<__nv_bfloat16>& r) {
+    asm volatile("ld.global.nc.L1::evict_first.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.v.x), "=r"(r.v.y), "=r"(r.v.z), "=r"(r.v.w) : "l"(p));
+}
+__device__ __forceinline__ void load_raw_stream(const float* __restrict__ p, RawChunk<float>& r) {
+    asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w) : "l"(p));
+    asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p + 4));
+}
 __device__ __forceinline__ void zero_raw(RawChunk<__nv_bfloat16>& r) { r.v = make_uint4(0, 0, 0, 0); }
 __device__ __forceinline__ void zero_raw(RawChunk<float>& r) { r.a = make_float4(0, 0, 0, 0); r.b = r.a; }
 __device__ __forceinline__ void raw_to_f32(const RawChunk<__nv_bfloat16>& r, float* x) {
